@@ -1,0 +1,508 @@
+// Memory-bound elementwise / reduction kernels of the StyleGAN2 hot path (channels-last fp32).
+// Roofline for all of them is HBM: algorithmic bytes = inputs read once + outputs written once.
+#include "common.cuh"
+
+namespace gifb200 {
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;
+
+// ------------------------------------------------------------------------------------------------ bias_act
+// t = x*rowscale[b,c] + add + bias[c]; y = lrelu(t)*gain.  One float4 (4 channels) per thread-iteration,
+// grid-stride over rows so that the grid is a multiple of the SM count.
+template <bool VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(const float* __restrict__ x, const float* __restrict__ rowscale,
+                                                       const float* __restrict__ add, const float* __restrict__ bias,
+                                                       float* __restrict__ y, long long total, int P, int C, float slope,
+                                                       float gain, int rtf32) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (VEC) {
+        const long long nvec = total >> 2;
+        const int c4n = C >> 2;
+        for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            const int c = static_cast<int>(v % c4n) << 2;
+            float4 t = __ldcs(reinterpret_cast<const float4*>(x) + v);
+            if (rowscale) {
+                const long long b = (v / c4n) / P;
+                const float4 s = *reinterpret_cast<const float4*>(rowscale + b * C + c);
+                t.x *= s.x; t.y *= s.y; t.z *= s.z; t.w *= s.w;
+            }
+            if (add) {
+                const float4 a = __ldcs(reinterpret_cast<const float4*>(add) + v);
+                t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+            }
+            if (bias) {
+                const float4 bb = *reinterpret_cast<const float4*>(bias + c);
+                t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+            }
+            t.x = (t.x > 0.f ? t.x : t.x * slope) * gain;
+            t.y = (t.y > 0.f ? t.y : t.y * slope) * gain;
+            t.z = (t.z > 0.f ? t.z : t.z * slope) * gain;
+            t.w = (t.w > 0.f ? t.w : t.w * slope) * gain;
+            if (rtf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+            reinterpret_cast<float4*>(y)[v] = t;
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c = static_cast<int>(i % C);
+            float t = x[i];
+            if (rowscale) t *= rowscale[((i / C) / P) * C + c];
+            if (add) t += add[i];
+            if (bias) t += bias[c];
+            t = (t > 0.f ? t : t * slope) * gain;
+            y[i] = rtf32 ? round_tf32(t) : t;
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                      float* __restrict__ gx, long long n, float slope, float gain,
+                                                      int rtf32) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (VEC) {
+        const long long nvec = n >> 2;
+        for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            const float4 g = __ldcs(reinterpret_cast<const float4*>(gy) + v);
+            const float4 o = __ldcs(reinterpret_cast<const float4*>(y) + v);
+            float4 r;
+            r.x = g.x * gain * (o.x > 0.f ? 1.f : slope);
+            r.y = g.y * gain * (o.y > 0.f ? 1.f : slope);
+            r.z = g.z * gain * (o.z > 0.f ? 1.f : slope);
+            r.w = g.w * gain * (o.w > 0.f ? 1.f : slope);
+            if (rtf32) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+            reinterpret_cast<float4*>(gx)[v] = r;
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        {
+            const float r = gy[i] * gain * (y[i] > 0.f ? 1.f : slope);
+            gx[i] = rtf32 ? round_tf32(r) : r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// out[g,c] = sum_r x[g,r,c].  Block = 32 (channels) x 8 (row lanes); grid = (C/32, row chunks, G); partial sums
+// are combined with one atomicAdd per (block, channel) into the zero-initialised output.
+__global__ void __launch_bounds__(256) rows_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows,
+                                                       int C, int rows_per_block) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int g = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    if (c < C) {
+        const float* base = x + (static_cast<long long>(g) * rows) * C + c;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += base[static_cast<long long>(r) * C];
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        atomicAdd(out + static_cast<long long>(g) * C + c, t);
+    }
+}
+
+// out[b,c] = sum_p a[b,p,c]*b2[b,p,c]  (same decomposition)
+__global__ void __launch_bounds__(256) spatial_dot_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                          float* __restrict__ out, int rows, int C, int rows_per_block) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int g = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    if (c < C) {
+        const long long base = (static_cast<long long>(g) * rows) * C + c;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const long long i = base + static_cast<long long>(r) * C;
+            acc += a[i] * b2[i];
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        atomicAdd(out + static_cast<long long>(g) * C + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ chan_scale
+template <bool VEC>
+__global__ void __launch_bounds__(256) chan_scale_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                         float* __restrict__ y, long long total, int P, int C,
+                                                         int rtf32) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (VEC) {
+        const long long nvec = total >> 2;
+        const int c4n = C >> 2;
+        for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            const int c = static_cast<int>(v % c4n) << 2;
+            const long long b = (v / c4n) / P;
+            float4 t = __ldcs(reinterpret_cast<const float4*>(x) + v);
+            const float4 sc = *reinterpret_cast<const float4*>(s + b * C + c);
+            t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
+            if (rtf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+            reinterpret_cast<float4*>(y)[v] = t;
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+            float t = x[i] * s[((i / C) / P) * C + (i % C)];
+            y[i] = rtf32 ? round_tf32(t) : t;
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                    float* __restrict__ y, long long n, float alpha, float beta,
+                                                    int rtf32) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (VEC) {
+        const long long nvec = n >> 2;
+        for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            float4 t = __ldcs(reinterpret_cast<const float4*>(a) + v);
+            t.x *= alpha; t.y *= alpha; t.z *= alpha; t.w *= alpha;
+            if (b) {
+                const float4 u = __ldcs(reinterpret_cast<const float4*>(b) + v);
+                t.x += beta * u.x; t.y += beta * u.y; t.z += beta * u.z; t.w += beta * u.w;
+            }
+            if (rtf32) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+            reinterpret_cast<float4*>(y)[v] = t;
+        }
+    } else {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        {
+            const float t = alpha * a[i] + (b ? beta * b[i] : 0.f);
+            y[i] = rtf32 ? round_tf32(t) : t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ demod
+// One warp per (b,o): lanes stride over i, shuffle-reduce sum_i s[b,i]^2 q[o,i].
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ s, const float* __restrict__ q,
+                                                    float* __restrict__ d, int B, int Ci, int Co, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B * Co) return;
+    const int b = warp / Co, o = warp % Co;
+    const float* sr = s + static_cast<long long>(b) * Ci;
+    const float* qr = q + static_cast<long long>(o) * Ci;
+    float acc = 0.f;
+    for (int i = lane; i < Ci; i += 32) {
+        const float sv = sr[i];
+        acc += sv * sv * qr[i];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) d[warp] = rsqrtf(acc + eps);
+}
+
+// ------------------------------------------------------------------------------------------------ ToRGB
+// y[b,p,0..2] = sum_i x[b,p,i]*ws[b,k,i].  One warp per pixel group: each lane strides the channel dim with float4,
+// three shuffle reductions per pixel.  x is read exactly once (HBM-bound: C*4 bytes/pixel in, 12 out).
+__global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ws,
+                                                        float* __restrict__ y, int B, int P, int C) {
+    extern __shared__ float sw[];  // 3*C weights of this sample
+    const int b = blockIdx.y;
+    const float* wsb = ws + static_cast<long long>(b) * 3 * C;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = wsb[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int p = blockIdx.x * nwarp + warp; p < P; p += gridDim.x * nwarp) {
+        const float* xr = x + (static_cast<long long>(b) * P + p) * C;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if ((C & 3) == 0) {
+            for (int i = lane * 4; i < C; i += 128) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(xr + i));
+                a0 += v.x * sw[i] + v.y * sw[i + 1] + v.z * sw[i + 2] + v.w * sw[i + 3];
+                a1 += v.x * sw[C + i] + v.y * sw[C + i + 1] + v.z * sw[C + i + 2] + v.w * sw[C + i + 3];
+                a2 += v.x * sw[2 * C + i] + v.y * sw[2 * C + i + 1] + v.z * sw[2 * C + i + 2] + v.w * sw[2 * C + i + 3];
+            }
+        } else {
+            for (int i = lane; i < C; i += 32) {
+                const float v = xr[i];
+                a0 += v * sw[i]; a1 += v * sw[C + i]; a2 += v * sw[2 * C + i];
+            }
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) {
+            float* yr = y + (static_cast<long long>(b) * P + p) * 3;
+            yr[0] = a0; yr[1] = a1; yr[2] = a2;
+        }
+    }
+}
+
+// gx[b,p,i] = sum_k gy[b,p,k]*ws[b,k,i]
+__global__ void __launch_bounds__(256) torgb_bwd_x_kernel(const float* __restrict__ gy, const float* __restrict__ ws,
+                                                          float* __restrict__ gx, int B, int P, int C) {
+    extern __shared__ float sw[];
+    const int b = blockIdx.y;
+    const float* wsb = ws + static_cast<long long>(b) * 3 * C;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) sw[i] = wsb[i];
+    __syncthreads();
+    const long long total = static_cast<long long>(P) * C;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(e / C), i = static_cast<int>(e % C);
+        const float* g = gy + (static_cast<long long>(b) * P + p) * 3;
+        gx[static_cast<long long>(b) * total + e] = g[0] * sw[i] + g[1] * sw[C + i] + g[2] * sw[2 * C + i];
+    }
+}
+
+// gws[b,k,i] = sum_p gy[b,p,k]*x[b,p,i]   (block: 32 channels x 8 row lanes, atomics into zeroed output)
+__global__ void __launch_bounds__(256) torgb_bwd_w_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                          float* __restrict__ gws, int P, int C, int rows_per_block) {
+    __shared__ float sm[3][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(P, r0 + rows_per_block);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (c < C) {
+        for (int p = r0 + threadIdx.y; p < r1; p += 8) {
+            const long long row = static_cast<long long>(b) * P + p;
+            const float v = x[row * C + c];
+            const float* g = gy + row * 3;
+            a0 += v * g[0]; a1 += v * g[1]; a2 += v * g[2];
+        }
+    }
+    sm[0][threadIdx.y][threadIdx.x] = a0;
+    sm[1][threadIdx.y][threadIdx.x] = a1;
+    sm[2][threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y < 3 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[threadIdx.y][j][threadIdx.x];
+        atomicAdd(gws + (static_cast<long long>(b) * 3 + threadIdx.y) * C + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cond pyramid
+// y[b,yo,xo,c] = mean of x[b, s*yo + s/2 - {1,0}, s*xo + s/2 - {1,0}, c]   (s >= 2, power of two); adjoint scatters.
+__global__ void __launch_bounds__(256) cond_down_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H,
+                                                        int W, int C, int s) {
+    const int Ho = H / s, Wo = W / s;
+    const long long total = static_cast<long long>(B) * Ho * Wo * C;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        long long r = e / C;
+        const int xo = static_cast<int>(r % Wo); r /= Wo;
+        const int yo = static_cast<int>(r % Ho);
+        const int b = static_cast<int>(r / Ho);
+        const int y0 = s * yo + s / 2 - 1, x0 = s * xo + s / 2 - 1;
+        const float* base = x + ((static_cast<long long>(b) * H + y0) * W + x0) * C + c;
+        const long long rs = static_cast<long long>(W) * C;
+        y[e] = 0.25f * (base[0] + base[C] + base[rs] + base[rs + C]);
+    }
+}
+
+__global__ void __launch_bounds__(256) cond_down_adj_kernel(float* __restrict__ gx, const float* __restrict__ gy, int B,
+                                                            int H, int W, int C, int s) {
+    const int Ho = H / s, Wo = W / s;
+    const long long total = static_cast<long long>(B) * H * W * C;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % C);
+        long long r = e / C;
+        const int xi = static_cast<int>(r % W); r /= W;
+        const int yi = static_cast<int>(r % H);
+        const int b = static_cast<int>(r / H);
+        const int ry = yi % s, rx = xi % s;
+        const bool hit = (ry == s / 2 - 1 || ry == s / 2) && (rx == s / 2 - 1 || rx == s / 2);
+        gx[e] = hit ? 0.25f * gy[((static_cast<long long>(b) * Ho + yi / s) * Wo + xi / s) * C + c] : 0.f;
+    }
+}
+
+static inline int grid_for(long long work_items, int per_block) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    const long long cap = static_cast<long long>(kNumSMs) * 16;  // multiple of the SM count; grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace gifb200
+
+using namespace gifb200;
+
+extern "C" {
+
+int gifb200_version(void) { return 100; }
+const char* gifb200_last_error(void) { return g_err; }
+long long gifb200_launch_count(void) { return g_launches; }
+
+int gifb200_bias_act(const float* x, const float* rowscale, const float* add, const float* bias, float* y, int B, int P,
+                     int C, float slope, float gain, int rtf32, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "bias_act: bad shape");
+    const long long total = static_cast<long long>(B) * P * C;
+    if (total == 0) return GIFB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y) && (!add || aligned16(add)) &&
+                     (!bias || aligned16(bias)) && (!rowscale || aligned16(rowscale));
+    if (vec)
+        bias_act_kernel<true><<<grid_for(total / 4, 256), 256, 0, st>>>(x, rowscale, add, bias, y, total, P, C, slope, gain, rtf32);
+    else
+        bias_act_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(x, rowscale, add, bias, y, total, P, C, slope, gain, rtf32);
+    GIFB200_LAUNCH_CHECK("bias_act_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_act_bwd(const float* gy, const float* y, float* gx, long long n, float slope, float gain, int rtf32,
+                    gifb200_stream_t stream) {
+    if (n <= 0) return GIFB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n % 4 == 0 && aligned16(gy) && aligned16(y) && aligned16(gx))
+        act_bwd_kernel<true><<<grid_for(n / 4, 256), 256, 0, st>>>(gy, y, gx, n, slope, gain, rtf32);
+    else
+        act_bwd_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(gy, y, gx, n, slope, gain, rtf32);
+    GIFB200_LAUNCH_CHECK("act_bwd_kernel");
+    return GIFB200_OK;
+}
+
+static int rows_split(int rows, int cblocks, int G, int* rows_per_block) {
+    // aim for ~4 blocks per SM in total
+    long long want = (static_cast<long long>(kNumSMs) * 4 + static_cast<long long>(cblocks) * G - 1) /
+                     (static_cast<long long>(cblocks) * G);
+    if (want < 1) want = 1;
+    int rpb = static_cast<int>((rows + want - 1) / want);
+    if (rpb < 64) rpb = 64;
+    *rows_per_block = rpb;
+    return (rows + rpb - 1) / rpb;
+}
+
+int gifb200_rows_sum(const float* x, float* out, int G, int rows, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(G >= 0 && rows >= 0 && C > 0, GIFB200_E_SHAPE, "rows_sum: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (G == 0) return GIFB200_OK;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(G) * C, st);
+    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "rows_sum memset", cudaGetErrorString(e));
+    if (rows == 0) return GIFB200_OK;
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(rows, cb, G, &rpb);
+    GIFB200_REQUIRE(G <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "rows_sum: grid too large");
+    rows_sum_kernel<<<dim3(cb, rb, G), dim3(32, 8), 0, st>>>(x, out, rows, C, rpb);
+    GIFB200_LAUNCH_CHECK("rows_sum_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "spatial_dot: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) return GIFB200_OK;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(B) * C, st);
+    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "spatial_dot memset", cudaGetErrorString(e));
+    if (P == 0) return GIFB200_OK;
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(P, cb, B, &rpb);
+    GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "spatial_dot: grid too large");
+    spatial_dot_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(a, b2, out, P, C, rpb);
+    GIFB200_LAUNCH_CHECK("spatial_dot_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_chan_scale(const float* x, const float* s, float* y, int B, int P, int C, int rtf32,
+                       gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "chan_scale: bad shape");
+    const long long total = static_cast<long long>(B) * P * C;
+    if (total == 0) return GIFB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (C % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(s))
+        chan_scale_kernel<true><<<grid_for(total / 4, 256), 256, 0, st>>>(x, s, y, total, P, C, rtf32);
+    else
+        chan_scale_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(x, s, y, total, P, C, rtf32);
+    GIFB200_LAUNCH_CHECK("chan_scale_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_axpby(const float* a, const float* b, float* y, long long n, float alpha, float beta, int rtf32,
+                  gifb200_stream_t stream) {
+    if (n <= 0) return GIFB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n % 4 == 0 && aligned16(a) && aligned16(y) && (!b || aligned16(b)))
+        axpby_kernel<true><<<grid_for(n / 4, 256), 256, 0, st>>>(a, b, y, n, alpha, beta, rtf32);
+    else
+        axpby_kernel<false><<<grid_for(n, 256), 256, 0, st>>>(a, b, y, n, alpha, beta, rtf32);
+    GIFB200_LAUNCH_CHECK("axpby_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_demod(const float* s, const float* q, float* d, int B, int Ci, int Co, float eps, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && Ci > 0 && Co > 0, GIFB200_E_SHAPE, "demod: bad shape");
+    if (B == 0) return GIFB200_OK;
+    const long long warps = static_cast<long long>(B) * Co;
+    demod_kernel<<<cdiv(warps * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(s, q, d, B, Ci, Co, eps);
+    GIFB200_LAUNCH_CHECK("demod_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_torgb_fwd(const float* x, const float* ws, float* y, int B, int P, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0 && C <= 4096, GIFB200_E_SHAPE, "torgb_fwd: bad shape");
+    GIFB200_REQUIRE(B <= 65535, GIFB200_E_SHAPE, "torgb_fwd: batch too large");
+    if (B == 0 || P == 0) return GIFB200_OK;
+    GIFB200_REQUIRE(C % 4 != 0 || aligned16(x), GIFB200_E_ALIGN, "torgb_fwd: x not 16B aligned");
+    int gx = cdiv(P, 8 * 4);
+    const int cap = max(1, kNumSMs * 8 / B);
+    if (gx > cap) gx = cap;
+    torgb_fwd_kernel<<<dim3(gx, B), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, ws, y, B, P, C);
+    GIFB200_LAUNCH_CHECK("torgb_fwd_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_torgb_bwd_x(const float* gy, const float* ws, float* gx, int B, int P, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0 && C <= 4096, GIFB200_E_SHAPE, "torgb_bwd_x: bad shape");
+    GIFB200_REQUIRE(B <= 65535, GIFB200_E_SHAPE, "torgb_bwd_x: batch too large");
+    if (B == 0 || P == 0) return GIFB200_OK;
+    int g = cdiv(static_cast<long long>(P) * C, 256 * 4);
+    const int cap = max(1, kNumSMs * 8 / B);
+    if (g > cap) g = cap;
+    torgb_bwd_x_kernel<<<dim3(g, B), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(gy, ws, gx, B, P, C);
+    GIFB200_LAUNCH_CHECK("torgb_bwd_x_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_torgb_bwd_w(const float* gy, const float* x, float* gws, int B, int P, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "torgb_bwd_w: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) return GIFB200_OK;
+    cudaError_t e = cudaMemsetAsync(gws, 0, sizeof(float) * static_cast<size_t>(B) * 3 * C, st);
+    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "torgb_bwd_w memset", cudaGetErrorString(e));
+    if (P == 0) return GIFB200_OK;
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(P, cb, B, &rpb);
+    GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "torgb_bwd_w: grid too large");
+    torgb_bwd_w_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gy, x, gws, P, C, rpb);
+    GIFB200_LAUNCH_CHECK("torgb_bwd_w_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_cond_down(float* x, float* y, int B, int H, int W, int C, int s, int adjoint, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && H > 0 && W > 0 && C > 0, GIFB200_E_SHAPE, "cond_down: bad shape");
+    GIFB200_REQUIRE(s >= 2 && (s & (s - 1)) == 0 && H % s == 0 && W % s == 0, GIFB200_E_SHAPE,
+                    "cond_down: s must be a power of two >= 2 dividing H and W");
+    if (B == 0) return GIFB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!adjoint) {
+        const long long total = static_cast<long long>(B) * (H / s) * (W / s) * C;
+        cond_down_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, B, H, W, C, s);
+        GIFB200_LAUNCH_CHECK("cond_down_kernel");
+    } else {
+        const long long total = static_cast<long long>(B) * H * W * C;
+        cond_down_adj_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, y, B, H, W, C, s);
+        GIFB200_LAUNCH_CHECK("cond_down_adj_kernel");
+    }
+    return GIFB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// Small dense fp32 GEMM for EqualLinear (mapping network 512x512, modulation 512xCi, D head 8192x512):
+// C[M,N] = alpha * op(A) op(B).  32x32 tiles, 256 threads, 2x2 micro-tiles.  These GEMMs are tiny
+// (<= 0.3 GFLOP per step in total) so a SIMT kernel is the right tool; tcgen05 is reserved for the convolutions.
+#include "common.cuh"
+
+namespace gifb200 {
+
+__global__ void __launch_bounds__(256) sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha,
+                                                    const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                    int ldb, float* __restrict__ C, int ldc) {
+    __shared__ float As[32][33];  // [k][m]
+    __shared__ float Bs[32][33];  // [k][n]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int e = threadIdx.x; e < 1024; e += 256) {
+            // read along the contiguous dimension of each operand
+            int kk, mm;
+            if (transA) { mm = e & 31; kk = e >> 5; } else { kk = e & 31; mm = e >> 5; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            float v = 0.f;
+            if (gm < M && gk < K) v = transA ? A[static_cast<long long>(gk) * lda + gm] : A[static_cast<long long>(gm) * lda + gk];
+            As[kk][mm] = v;
+            int kb, nn;
+            if (transB) { kb = e & 31; nn = e >> 5; } else { nn = e & 31; kb = e >> 5; }
+            const int gn = n0 + nn, gkb = k0 + kb;
+            float w = 0.f;
+            if (gn < N && gkb < K) w = transB ? B[static_cast<long long>(gn) * ldb + gkb] : B[static_cast<long long>(gkb) * ldb + gn];
+            Bs[kb][nn] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+            const float b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gm = m0 + ty * 2 + i, gn = n0 + tx * 2 + j;
+            if (gm < M && gn < N) C[static_cast<long long>(gm) * ldc + gn] = alpha * acc[i][j];
+        }
+}
+
+}  // namespace gifb200
+
+using namespace gifb200;
+
+extern "C" int gifb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                             const float* B, int ldb, float* C, int ldc, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(M >= 0 && N >= 0 && K >= 0, GIFB200_E_SHAPE, "sgemm: bad shape");
+    if (M == 0 || N == 0) return GIFB200_OK;
+    GIFB200_REQUIRE(cdiv(M, 32) <= 65535, GIFB200_E_SHAPE, "sgemm: M too large");
+    sgemm_kernel<<<dim3(cdiv(N, 32), cdiv(M, 32)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        transA, transB, M, N, K, alpha, A, lda, B, ldb, C, ldc);
+    GIFB200_LAUNCH_CHECK("sgemm_kernel");
+    return GIFB200_OK;
+}

@@ -1,0 +1,85 @@
+// upfirdn2d: zero-insert upsample, pad/crop, small FIR, decimate -- one pass, channels-last.
+// HBM-bound: algorithmic bytes = input + output (taps are re-read from L1/L2, never from HBM).
+#include "common.cuh"
+
+namespace gifb200 {
+
+struct UpfirdnParams {
+    int B, Hi, Wi, C, Ho, Wo, kh, kw, up, down, py0, px0, flip, rtf32;
+};
+
+// VEC: 4 channels per thread (C % 4 == 0).  Thread -> (pixel, channel group); consecutive threads walk the channel
+// dimension first, so every tap is a fully coalesced 16B-per-lane read.
+template <bool VEC>
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                                                        float* __restrict__ y, UpfirdnParams p) {
+    __shared__ float sk[64];
+    if (threadIdx.x < p.kh * p.kw) {
+        const int a = threadIdx.x / p.kw, b = threadIdx.x % p.kw;
+        // K[a][b] = flip ? kernel[kh-1-a][kw-1-b] : kernel[a][b]
+        sk[threadIdx.x] = p.flip ? kernel[(p.kh - 1 - a) * p.kw + (p.kw - 1 - b)] : kernel[threadIdx.x];
+    }
+    __syncthreads();
+    const int cg = VEC ? (p.C >> 2) : p.C;
+    const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * cg;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % cg);
+        long long r = e / cg;
+        const int xo = static_cast<int>(r % p.Wo); r /= p.Wo;
+        const int yo = static_cast<int>(r % p.Ho);
+        const int b = static_cast<int>(r / p.Ho);
+        // position in the zero-inserted grid touched by tap a: uy = yo*down + (kh-1-a) - py0
+        const int uy_hi = yo * p.down + (p.kh - 1) - p.py0;  // a = 0
+        const int ux_hi = xo * p.down + (p.kw - 1) - p.px0;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < p.kh; ++a) {
+            const int uy = uy_hi - a;
+            if (uy < 0 || uy % p.up != 0) continue;
+            const int iy = uy / p.up;
+            if (iy >= p.Hi) continue;
+            for (int bb = 0; bb < p.kw; ++bb) {
+                const int ux = ux_hi - bb;
+                if (ux < 0 || ux % p.up != 0) continue;
+                const int ix = ux / p.up;
+                if (ix >= p.Wi) continue;
+                const float kv = sk[a * p.kw + bb];
+                const long long off = ((static_cast<long long>(b) * p.Hi + iy) * p.Wi + ix) * p.C;
+                if (VEC) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(x + off) + c);
+                    acc.x += kv * v.x; acc.y += kv * v.y; acc.z += kv * v.z; acc.w += kv * v.w;
+                } else {
+                    acc.x += kv * __ldg(x + off + c);
+                }
+            }
+        }
+        if (p.rtf32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+        if (VEC) reinterpret_cast<float4*>(y)[e] = acc;
+        else y[e] = acc.x;
+    }
+}
+
+}  // namespace gifb200
+
+using namespace gifb200;
+
+extern "C" int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, int B, int Hi, int Wi, int C, int Ho,
+                                 int Wo, int kh, int kw, int up, int down, int pad_y0, int pad_x0, int flip,
+                                 int round_tf32, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && Hi > 0 && Wi > 0 && C > 0 && Ho >= 0 && Wo >= 0, GIFB200_E_SHAPE, "upfirdn2d: bad shape");
+    GIFB200_REQUIRE(kh >= 1 && kw >= 1 && kh <= 8 && kw <= 8, GIFB200_E_SHAPE, "upfirdn2d: kernel must be <= 8x8");
+    GIFB200_REQUIRE(up >= 1 && down >= 1, GIFB200_E_SHAPE, "upfirdn2d: up/down must be >= 1");
+    const long long total = static_cast<long long>(B) * Ho * Wo * C;
+    if (total == 0) return GIFB200_OK;
+    UpfirdnParams p{B, Hi, Wi, C, Ho, Wo, kh, kw, up, down, pad_y0, pad_x0, flip, round_tf32};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y);
+    const long long items = vec ? total / 4 : total;
+    long long blocks = (items + 255) / 256;
+    const long long cap = static_cast<long long>(kNumSMs) * 32;
+    if (blocks > cap) blocks = cap;
+    if (vec) upfirdn2d_kernel<true><<<static_cast<int>(blocks), 256, 0, st>>>(x, kernel, y, p);
+    else upfirdn2d_kernel<false><<<static_cast<int>(blocks), 256, 0, st>>>(x, kernel, y, p);
+    GIFB200_LAUNCH_CHECK("upfirdn2d_kernel");
+    return GIFB200_OK;
+}

@@ -1,0 +1,54 @@
+"""Synthetic FLAME-shaped workload for the rasteriser (BASELINE.json configs[3]).
+
+The FLAME model itself (generic_model.pkl, texture space) is licence-gated and absent from the reference tree, so
+"random FLAME params" drive a FLAME-*shaped* linear decoder on the real FLAME topology (V=5023, F=9976; template from
+my_utils/photometric_optimization/data/head_template_mesh.obj, stored as tests/golden/flame_template.npz):
+    verts = T + sum_j beta_j S_j,  beta ~ N(0,1) (B,150),  S ~ N(0,(2 mm)^2)
+followed by the reference's camera path: a random head rotation (cf. plots/generate_random_samples.py:107-108),
+util.batch_orth_proj (util.py:73-83) + the y/z flip of gif_helper.py:26-27, and the pixel mapping of
+visibility.py:38-40 (x*w/2+w/2, y*h/2+h/2, z-min(z)+1).
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+_TEMPLATE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                         "flame_template.npz")
+_cache = {}
+
+
+def flame_topology():
+    if "t" not in _cache:
+        z = np.load(_TEMPLATE)
+        v = torch.from_numpy(z["vertices"].astype(np.float32))
+        _cache["t"] = (v - v.mean(0, keepdim=True), torch.from_numpy(z["faces"].astype(np.int64)))
+    return _cache["t"]
+
+
+def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
+    """-> face_vertices (B,F,3,3) fp32 in pixel space, face_colors (B,F,3,3) in [0,1]."""
+    tmpl, faces = flame_topology()
+    g = torch.Generator().manual_seed(1234 + seed)
+    basis = torch.randn(150, tmpl.shape[0] * 3, generator=torch.Generator().manual_seed(7)) * 0.002
+    beta = torch.randn(batch, 150, generator=g)
+    verts = tmpl[None] + (beta @ basis).reshape(batch, -1, 3)
+    yaw = (torch.rand(batch, generator=g) * 2 - 1) * (math.pi / 8)
+    pitch = torch.rand(batch, generator=g) * (math.pi / 12)
+    cy, sy, cp, sp = torch.cos(yaw), torch.sin(yaw), torch.cos(pitch), torch.sin(pitch)
+    zero, one = torch.zeros_like(cy), torch.ones_like(cy)
+    ry = torch.stack([cy, zero, sy, zero, one, zero, -sy, zero, cy], -1).reshape(batch, 3, 3)
+    rx = torch.stack([one, zero, zero, zero, cp, -sp, zero, sp, cp], -1).reshape(batch, 3, 3)
+    verts = verts @ (rx @ ry).transpose(1, 2)
+    cam = torch.cat([torch.rand(batch, 1, generator=g) * 3 + 7, (torch.rand(batch, 2, generator=g) * 2 - 1) * 0.02], 1)
+    proj = torch.cat([verts[..., :2] + cam[:, None, 1:], verts[..., 2:]], -1) * cam[:, None, 0:1]   # batch_orth_proj
+    proj[..., 1:] = -proj[..., 1:]                                                                   # gif_helper.py:27
+    pix = proj.clone()
+    pix[..., 0] = proj[..., 0] * w / 2 + w / 2
+    pix[..., 1] = proj[..., 1] * h / 2 + h / 2
+    pix[..., 2] = proj[..., 2] - proj[..., 2].min() + 1
+    vcol = torch.rand(batch, tmpl.shape[0], 3, generator=g)
+    fv = pix[:, faces]          # (B,F,3,3)
+    fc = vcol[:, faces]
+    return fv.contiguous().to(device), fc.contiguous().to(device)

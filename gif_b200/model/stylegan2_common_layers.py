@@ -1,0 +1,427 @@
+"""Operator library with the API of the reference's model/stylegan2_common_layers.py ("cl.py").
+
+Every class keeps the reference's name, constructor signature, parameter/buffer names and shapes (so reference
+checkpoints load) and its NCHW tensor interface; the arithmetic runs on the sm_100a kernels of
+libgifb200.so through gif_b200.ops (channels-last internally; the NCHW tensors these modules return are views of
+channels-last storage, so chaining modules costs no layout conversions).
+
+Formulation of ModulatedConv2d (cl.py:250-349): instead of materialising a per-sample weight (B,Co,Ci,k,k) and
+running a grouped convolution, the style modulates the *input* (x * s[b,i]), one shared-weight convolution runs on
+the tensor cores, and the demodulation coefficient d[b,o] scales the *output* (equal to the
+reference to fp32 rounding).
+"""
+import math
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def make_kernel(k):
+    """cl.py:83-91."""
+    k = torch.tensor(k, dtype=torch.float32)
+    if k.ndim == 1:
+        k = k[None, :] * k[:, None]
+    k /= k.sum()
+    return k
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """cl.py:42-72 (NCHW in, NCHW view out)."""
+    return ops.to_nchw_view(ops.upfirdn2d(ops.to_nhwc(input), kernel, up=up, down=down, pad=pad))
+
+
+class FusedLeakyReLU(nn.Module):
+    """cl.py:22-39: scale * leaky_relu(x + bias)."""
+
+    def __init__(self, channel, negative_slope=0.2, scale=2 ** 0.5):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(1, channel, 1, 1))
+        self.negative_slope = negative_slope
+        self.scale = scale
+
+    def forward(self, input, _rt=False):
+        return ops.to_nchw_view(ops.bias_act(ops.to_nhwc(input), self.bias, self.negative_slope, self.scale, rt=_rt))
+
+
+class PixelNorm(nn.Module):
+    """cl.py:75-80 (a (B,512) vector op: plain torch glue)."""
+
+    def forward(self, input):
+        return input * torch.rsqrt(torch.mean(input ** 2, dim=1, keepdim=True) + 1e-8)
+
+
+class Upsample(nn.Module):
+    """cl.py:94-112."""
+
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        kernel = make_kernel(kernel) * (factor ** 2)
+        self.register_buffer('kernel', kernel)
+        p = kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=self.factor, down=1, pad=self.pad)
+
+
+class Downsample(nn.Module):
+    """cl.py:115-133."""
+
+    def __init__(self, kernel, factor=2):
+        super().__init__()
+        self.factor = factor
+        kernel = make_kernel(kernel)
+        self.register_buffer('kernel', kernel)
+        p = kernel.shape[0] - factor
+        self.pad = ((p + 1) // 2, p // 2)
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, up=1, down=self.factor, pad=self.pad)
+
+
+class Blur(nn.Module):
+    """cl.py:136-152."""
+
+    def __init__(self, kernel, pad, upsample_factor=1):
+        super().__init__()
+        kernel = make_kernel(kernel)
+        if upsample_factor > 1:
+            kernel = kernel * (upsample_factor ** 2)
+        self.register_buffer('kernel', kernel)
+        self.pad = pad
+
+    def forward(self, input):
+        return upfirdn2d(input, self.kernel, pad=self.pad)
+
+
+def _conv_mode(kernel_size, stride, padding):
+    if stride == 1 and padding == kernel_size // 2:
+        return ops.S1
+    if stride == 2 and padding == 0:
+        return ops.S2
+    raise NotImplementedError(f"gif_b200 convolution: (k={kernel_size}, stride={stride}, padding={padding}) is not on "
+                              "the GIF hot path (supported: stride 1 with 'same' padding, stride 2 without padding)")
+
+
+class EqualConv2d(nn.Module):
+    """cl.py:155-190."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_channel, in_channel, kernel_size, kernel_size))
+        self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
+        self.stride = stride
+        self.padding = padding
+        self.kernel_size = kernel_size
+        self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
+
+    def forward_nhwc(self, x):
+        mode = _conv_mode(self.kernel_size, self.stride, self.padding)
+        y = ops.conv2d(x, ops.prep_weight(self.weight, self.scale), self.kernel_size, mode)
+        if self.bias is not None:
+            y = ops.bias_act(y, self.bias, slope=1.0, gain=1.0)
+        return y
+
+    def forward(self, input):
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input)))
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},'
+                f' {self.weight.shape[2]}, stride={self.stride}, padding={self.padding})')
+
+
+class EqualLinear(nn.Module):
+    """cl.py:193-235."""
+
+    def __init__(self, in_dim, out_dim, bias=True, bias_init=0, lr_mul=1, activation=None, scale_weight=1.0,
+                 apply_sqrt2_fac_in_eq_lin=False):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(out_dim, in_dim).div_(lr_mul / scale_weight))
+        self.bias = nn.Parameter(torch.zeros(out_dim).fill_(bias_init)) if bias else None
+        self.activation = activation
+        self.scale = (1 / math.sqrt(in_dim)) * lr_mul
+        self.lr_mul = lr_mul
+        self.apply_sqrt2_fac_in_eq_lin = apply_sqrt2_fac_in_eq_lin
+
+    def forward(self, input):
+        x = input.reshape(-1, input.shape[-1])
+        y = ops.matmul(x, self.weight, trans_b=True, alpha=self.scale)
+        bias = None if self.bias is None else self.bias * self.lr_mul
+        if self.activation:
+            gain = 1.41421356237 if self.apply_sqrt2_fac_in_eq_lin else 1.0      # cl.py:221-222
+            y = ops.bias_act(y, bias, slope=0.2, gain=gain)
+        elif bias is not None:
+            y = ops.bias_act(y, bias, slope=1.0, gain=1.0)
+        return y.reshape(input.shape[:-1] + (self.weight.shape[0],))
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]})'
+
+
+class ScaledLeakyReLU(nn.Module):
+    """cl.py:238-247."""
+
+    def __init__(self, negative_slope=0.2):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, input):
+        return ops.to_nchw_view(ops.bias_act(ops.to_nhwc(input), None, self.negative_slope, math.sqrt(2)))
+
+
+class ModulatedConv2d(nn.Module):
+    """cl.py:250-349."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
+                 downsample=False, blur_kernel=[1, 3, 3, 1], apply_sqrt2_fac_in_eq_lin=False):
+        super().__init__()
+        self.eps = 1e-8
+        self.kernel_size = kernel_size
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.upsample = upsample
+        self.downsample = downsample
+        if upsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) - (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2 + factor - 1, p // 2 + 1), upsample_factor=factor)
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            self.blur = Blur(blur_kernel, pad=((p + 1) // 2, p // 2))
+        fan_in = in_channel * kernel_size ** 2
+        self.scale = 1 / math.sqrt(fan_in)
+        self.padding = kernel_size // 2
+        self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
+        self.modulation = EqualLinear(style_dim, in_channel, bias_init=1,
+                                      apply_sqrt2_fac_in_eq_lin=apply_sqrt2_fac_in_eq_lin)
+        self.demodulate = demodulate
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, '
+                f'upsample={self.upsample}, downsample={self.downsample})')
+
+    def accumulate(self, x, style):
+        """NHWC x -> (acc, d): the un-demodulated shared-weight convolution of the modulated input (after the blur
+        of the upsample branch) and the demodulation coefficients d[b,o] (None if demodulate=False)."""
+        s = self.modulation(style)                                        # (B,Ci)  cl.py:311
+        wt = ops.prep_weight(self.weight[0], self.scale)                  # (T,Co,Ci) = W~ tap-major
+        k = self.kernel_size
+        if k == 1 and self.out_channel == 3 and not (self.upsample or self.downsample):
+            # ToRGB: per-sample 1x1 weights ws[b,c,i] = W~[c,i] s[b,i] (3*Ci numbers per sample), no modulated copy of x
+            acc = ops.torgb(x, wt[0][None] * s[:, None, :])
+        else:
+            xs = ops.chan_scale(x, s, ops.tf32_enabled())
+            if self.upsample:
+                acc = ops.conv2d(xs, wt, k, ops.T2)                       # (2H+1)^2  cl.py:322-331
+                acc = ops.upfirdn2d(acc, self.blur.kernel, pad=self.blur.pad)   # cl.py:333
+            elif self.downsample:
+                xs = ops.upfirdn2d(xs, self.blur.kernel, pad=self.blur.pad, rt=ops.tf32_enabled())
+                acc = ops.conv2d(xs, wt, k, ops.S2)                       # cl.py:335-341
+            else:
+                acc = ops.conv2d(xs, wt, k, ops.S1)                       # cl.py:343-347
+        d = None
+        if self.demodulate:
+            q = (wt * wt).sum(dim=0)                                      # (Co,Ci) = sum_taps W~^2
+            d = ops.demod(s, q, self.eps)                                 # cl.py:315-316
+        return acc, d
+
+    def forward_nhwc(self, x, style):
+        acc, d = self.accumulate(x, style)
+        return acc if d is None else ops.chan_scale(acc, d)
+
+    def forward(self, input, style):
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input), style))
+
+
+class NoiseInjection(nn.Module):
+    """cl.py:388-431: image + Conv3x3(ReLU(Conv3x3(ReLU(Conv3x3(cond))))) with plain nn.Conv2d parameters."""
+
+    @staticmethod
+    def small_init_weights(m):
+        if hasattr(m, 'weight'):
+            m.weight.data = torch.randn_like(m.weight) / 100
+        if hasattr(m, 'bias'):
+            m.bias.data.fill_(0.0001)
+
+    def __init__(self, noise_in_chalnnels, noise_out_channels):
+        super().__init__()
+        self.noise_in_chalnnels = noise_in_chalnnels
+        c = noise_in_chalnnels
+        self.noise_conv = nn.Sequential(
+            nn.Conv2d(in_channels=c, out_channels=2 * c, kernel_size=3, padding=1, dilation=1),
+            nn.ReLU(),
+            nn.Conv2d(in_channels=2 * c, out_channels=4 * c, kernel_size=3, padding=1, dilation=1),
+            nn.ReLU(),
+            nn.Conv2d(in_channels=4 * c, out_channels=noise_out_channels, kernel_size=3, padding=1, dilation=1),
+        )
+        self.noise_conv.apply(NoiseInjection.small_init_weights)
+
+    def convolved_noise_nhwc(self, noise):
+        """noise (B,r,r,c) NHWC -> (B,r,r,Co) NHWC *without* the last bias (returned separately for fusion)."""
+        c0, c2, c4 = self.noise_conv[0], self.noise_conv[2], self.noise_conv[4]
+        h = ops.conv2d(noise, ops.prep_weight(c0.weight), 3, ops.S1)
+        h = ops.bias_act(h, c0.bias, slope=0.0, gain=1.0)                 # + bias, ReLU
+        h = ops.conv2d(h, ops.prep_weight(c2.weight), 3, ops.S1)
+        h = ops.bias_act(h, c2.bias, slope=0.0, gain=1.0)
+        h = ops.conv2d(h, ops.prep_weight(c4.weight), 3, ops.S1)
+        return h, c4.bias
+
+    def forward(self, image, noise):
+        x = ops.to_nhwc(image)
+        if noise is None:
+            b, _, hh, ww = image.shape
+            noise = image.new_empty(b, self.noise_in_chalnnels, hh, ww).normal_()
+        h, b4 = self.convolved_noise_nhwc(ops.to_nhwc(noise))
+        # image + (h + bias): one fused pass (identity activation)
+        return ops.to_nchw_view(ops.bias_act(h, b4, slope=1.0, gain=1.0, add=x))
+
+
+class ConstantInput(nn.Module):
+    """cl.py:434-444."""
+
+    def __init__(self, channel, size=4):
+        super().__init__()
+        self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        return self.input.repeat(input.shape[0], 1, 1, 1)
+
+
+class StyledConv(nn.Module):
+    """cl.py:447-486: ModulatedConv2d -> NoiseInjection(cond) -> FusedLeakyReLU; the demodulation, the noise add, the
+    bias and the activation are ONE kernel (gifb200_bias_act) on the convolution's accumulator."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, noise_in_dims, style_dim=512, upsample=False,
+                 blur_kernel=[1, 3, 3, 1], demodulate=True, apply_sqrt2_fac_in_eq_lin=False):
+        super().__init__()
+        self.conv = ModulatedConv2d(in_channel, out_channel, kernel_size, style_dim, upsample=upsample,
+                                    blur_kernel=blur_kernel, demodulate=demodulate,
+                                    apply_sqrt2_fac_in_eq_lin=apply_sqrt2_fac_in_eq_lin)
+        self.noise = NoiseInjection(noise_in_dims, out_channel)
+        self.activate = FusedLeakyReLU(out_channel)
+
+    def forward_nhwc(self, x, style, noise_nhwc):
+        acc, d = self.conv.accumulate(x, style)
+        if noise_nhwc is None:
+            b, hh, ww, _ = acc.shape
+            noise_nhwc = acc.new_empty(b, hh, ww, self.noise.noise_in_chalnnels).normal_()
+        h, b4 = self.noise.convolved_noise_nhwc(noise_nhwc)
+        bias = self.activate.bias.reshape(-1) + b4                        # last noise-conv bias folds into the act bias
+        return ops.bias_act(acc, bias, self.activate.negative_slope, self.activate.scale, rowscale=d, add=h)
+
+    def forward(self, input, style, noise=None):
+        n = None if noise is None else ops.to_nhwc(noise)
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input), style, n))
+
+
+class ToRGB(nn.Module):
+    """cl.py:489-511."""
+
+    def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=[1, 3, 3, 1],
+                 apply_sqrt2_fac_in_eq_lin=False):
+        super().__init__()
+        if upsample:
+            self.upsample = Upsample(blur_kernel)
+        self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False,
+                                    apply_sqrt2_fac_in_eq_lin=apply_sqrt2_fac_in_eq_lin)
+        self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+    def forward_nhwc(self, x, style, skip):
+        acc, _ = self.conv.accumulate(x, style)
+        if skip is not None:
+            skip = ops.upfirdn2d(skip, self.upsample.kernel, up=self.upsample.factor, pad=self.upsample.pad)
+        return ops.bias_act(acc, self.bias, slope=1.0, gain=1.0, add=skip)   # + bias (+ upsampled skip), one pass
+
+    def forward(self, input, style, skip=None):
+        s = None if skip is None else ops.to_nhwc(skip)
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input), style, s))
+
+
+def get_w_frm_z(n_mlp, style_dim, lr_mlp=1, scale_weight=1.0):
+    """cl.py:514-533."""
+    if n_mlp > 0:
+        layers = [PixelNorm()]
+        for _ in range(n_mlp):
+            layers.append(EqualLinear(style_dim, style_dim, lr_mul=lr_mlp, activation='fused_lrelu',
+                                      scale_weight=scale_weight))
+        return nn.Sequential(*layers)
+
+    class Net(nn.Module):
+        def forward(self, *args):
+            return args[0]
+
+    return Net()
+
+
+class ConvLayer(nn.Sequential):
+    """cl.py:752-799: [Blur ->] EqualConv2d -> FusedLeakyReLU | ScaledLeakyReLU."""
+
+    def __init__(self, in_channel, out_channel, kernel_size, downsample=False, blur_kernel=[1, 3, 3, 1], bias=True,
+                 activate=True):
+        layers = []
+        if downsample:
+            factor = 2
+            p = (len(blur_kernel) - factor) + (kernel_size - 1)
+            layers.append(Blur(blur_kernel, pad=((p + 1) // 2, p // 2)))
+            stride = 2
+            self.padding = 0
+        else:
+            stride = 1
+            self.padding = kernel_size // 2
+        layers.append(EqualConv2d(in_channel, out_channel, kernel_size, padding=self.padding, stride=stride,
+                                  bias=bias and not activate))
+        if activate:
+            layers.append(FusedLeakyReLU(out_channel) if bias else ScaledLeakyReLU(0.2))
+        super().__init__(*layers)
+
+    def forward_nhwc(self, x, rt_out=False):
+        """Channels-last fast path used by ResBlock / Discriminator (same arithmetic as the Sequential)."""
+        tf32 = ops.tf32_enabled()
+        for layer in self:
+            if isinstance(layer, Blur):
+                conv = self[1]
+                if conv.kernel_size == 1:
+                    # blur(pad 1,1) then 1x1 stride-2 conv == FIR evaluated only at the even output sites
+                    # (upfirdn2d down=2), then a stride-1 1x1 conv: 4x fewer FIR outputs (cl.py:765-771,:776-786)
+                    x = ops.upfirdn2d(x, layer.kernel, down=2, pad=layer.pad, rt=tf32)
+                else:
+                    x = ops.upfirdn2d(x, layer.kernel, pad=layer.pad, rt=tf32)
+            elif isinstance(layer, EqualConv2d):
+                if layer.kernel_size == 1 and layer.stride == 2:
+                    y = ops.conv2d(x, ops.prep_weight(layer.weight, layer.scale), 1, ops.S1)
+                    x = y if layer.bias is None else ops.bias_act(y, layer.bias, slope=1.0, gain=1.0)
+                else:
+                    x = layer.forward_nhwc(x)
+            elif isinstance(layer, FusedLeakyReLU):
+                x = ops.bias_act(x, layer.bias, layer.negative_slope, layer.scale, rt=rt_out and tf32)
+            elif isinstance(layer, ScaledLeakyReLU):
+                x = ops.bias_act(x, None, layer.negative_slope, math.sqrt(2), rt=rt_out and tf32)
+            else:
+                raise TypeError(type(layer))
+        return x
+
+    def forward(self, input):
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input)))
+
+
+class ResBlock(nn.Module):
+    """cl.py:802-820."""
+
+    def __init__(self, in_channel, out_channel, blur_kernel=[1, 3, 3, 1]):
+        super().__init__()
+        self.conv1 = ConvLayer(in_channel, in_channel, 3)
+        self.conv2 = ConvLayer(in_channel, out_channel, 3, downsample=True)
+        self.skip = ConvLayer(in_channel, out_channel, 1, downsample=True, activate=False, bias=False)
+
+    def forward_nhwc(self, x):
+        out = self.conv2.forward_nhwc(self.conv1.forward_nhwc(x))
+        skip = self.skip.forward_nhwc(x)
+        return ops.axpby(out, skip, 1 / math.sqrt(2), 1 / math.sqrt(2), rt=ops.tf32_enabled())
+
+    def forward(self, input):
+        return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input)))

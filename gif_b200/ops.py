@@ -1,0 +1,559 @@
+"""torch.autograd wrappers over the C ABI (include/gifb200.h).
+
+Conventions
+  * activations are fp32 CUDA tensors in channels-last *physical* layout, shape (B, H, W, C), contiguous
+    ("NHWC"); the module classes in gif_b200/model convert from/to the reference's NCHW view at the boundary
+    (a zero-copy permute when the tensor came from one of these ops);
+  * every Function's ``backward`` is written in terms of other Functions of this file, so arbitrary-order
+    derivatives exist (R1 needs the double backward of every discriminator op, losses.py:91; the path-length
+    regulariser needs it for every generator op);
+  * there is no CPU / eager fallback: non-CUDA tensors raise.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream
+
+S1, S2, T2 = 0, 1, 2          # conv modes of gifb200_conv2d
+_ADJ_MODE = {S1: S1, S2: T2, T2: S2}
+CONV_IMPL = 0                 # 0 auto, 1 force SIMT fp32, 2 force tcgen05 (tests flip this)
+_PRECISION = "tf32"
+
+
+def set_precision(mode):
+    """"tf32": convolutions that qualify run on tcgen05 (kind::tf32, fp32 accumulate) and their operand producers
+    round to tf32; "fp32": every convolution runs on the exact-fp32 SIMT kernels (parity arbitration, odd shapes)."""
+    global CONV_IMPL, _PRECISION
+    if mode not in ("tf32", "fp32"):
+        raise ValueError(mode)
+    _PRECISION = mode
+    CONV_IMPL = 0 if mode == "tf32" else 1
+
+
+def get_precision():
+    return _PRECISION
+
+
+def tf32_enabled():
+    return _PRECISION == "tf32" and CONV_IMPL != 1
+
+
+def _tag(t, rounded):
+    """Marks a tensor whose values are exactly representable in tf32 (so a tcgen05 consumer needs no rounding pass)."""
+    if rounded:
+        t._gifb200_tf32 = True
+    return t
+
+
+def _is_tf32(t):
+    return getattr(t, "_gifb200_tf32", False)
+
+
+def _round_tf32_raw(x):
+    y = torch.empty_like(x)
+    check(lib.gifb200_axpby(ptr(x), None, ptr(y), x.numel(), 1.0, 0.0, 1, stream()), "gifb200_axpby(round)")
+    return y
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """A per-device scratch buffer, grown on demand (stream-ordered reuse: all our launches are on the current stream)."""
+    if nbytes == 0:
+        return None
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------- convolution
+def conv_out_size(hi, k, mode):
+    if mode == S1:
+        return hi
+    if mode == S2:
+        return (hi - k) // 2 + 1
+    return 2 * (hi - 1) + k
+
+
+def _conv_raw(x, w, k, mode, flip, transposed, out_hw):
+    require_cuda(x, w)
+    B, Hi, Wi, Ci = x.shape
+    T, R, S = w.shape
+    Co = R if not transposed else S
+    assert T == k * k and (S if not transposed else R) == Ci, f"weight {tuple(w.shape)} vs input channels {Ci}"
+    Ho, Wo = out_hw
+    y = torch.empty((B, Ho, Wo, Co), dtype=torch.float32, device=x.device)
+    nws = lib.gifb200_conv2d_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(transposed), CONV_IMPL)
+    if nws > 0 and not _is_tf32(x):          # tensor-core path: operands must be tf32-representable (see gifb200.h)
+        x = _tag(_round_tf32_raw(x), True)
+    ws = _workspace(nws, x.device)
+    check(lib.gifb200_conv2d(ptr(x), ptr(w), ptr(y), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip), int(transposed),
+                             CONV_IMPL, ptr(ws), nws, stream()), "gifb200_conv2d")
+    return y, x
+
+
+def _wgrad_raw(x, gy, k, mode, flip, transposed):
+    require_cuda(x, gy)
+    B, Hi, Wi, Ci = x.shape
+    _, Ho, Wo, Co = gy.shape
+    shape = (k * k, Ci, Co) if transposed else (k * k, Co, Ci)
+    gw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    impl = 1 if CONV_IMPL == 1 else 0
+    check(lib.gifb200_conv2d_wgrad(ptr(x), ptr(gy), ptr(gw), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip),
+                                   int(transposed), impl, None, 0, stream()), "gifb200_conv2d_wgrad")
+    return gw
+
+
+class _Conv(torch.autograd.Function):
+    """y = conv(x; W) with W addressed in the physical buffer w[T][R][S] (see gifb200.h)."""
+
+    @staticmethod
+    def forward(ctx, x, w, k, mode, flip, transposed, out_hw):
+        x, w = _c(x), _c(w)
+        y, x_used = _conv_raw(x, w, k, mode, flip, transposed, out_hw)
+        ctx.save_for_backward(x_used, w)          # the (possibly tf32-rounded) operand is what wgrad re-reads
+        ctx.cfg = (k, mode, flip, transposed, tuple(x.shape[1:3]), _is_tf32(x_used))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        k, mode, flip, transposed, in_hw, x_tf32 = ctx.cfg
+        _tag(x, x_tf32)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            # adj(S1, f, t) = (S1, !f, !t); adj(S2, f, t) = (T2, f, !t); adj(T2, f, t) = (S2, f, !t)
+            gx = _Conv.apply(gy, w, k, _ADJ_MODE[mode], (not flip) if mode == S1 else flip, not transposed, in_hw)
+        if ctx.needs_input_grad[1]:
+            gw = _ConvWgrad.apply(x, gy, k, mode, flip, transposed)
+        return gx, gw, None, None, None, None, None
+
+
+class _ConvWgrad(torch.autograd.Function):
+    """gw (physical layout of w) = d<gy, conv(x; w)>/dw -- bilinear in (x, gy)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, k, mode, flip, transposed):
+        x, gy = _c(x), _c(gy)
+        ctx.save_for_backward(x, gy)
+        ctx.cfg = (k, mode, flip, transposed)
+        return _wgrad_raw(x, gy, k, mode, flip, transposed)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        k, mode, flip, transposed = ctx.cfg
+        gx = ggy = None
+        if ctx.needs_input_grad[0]:   # <ggw, wgrad(x, gy)> = <gy, conv(x; ggw)>  ->  d/dx = adj conv of gy with ggw
+            gx = _Conv.apply(gy, ggw, k, _ADJ_MODE[mode], (not flip) if mode == S1 else flip, not transposed,
+                             tuple(x.shape[1:3]))
+        if ctx.needs_input_grad[1]:
+            ggy = _Conv.apply(x, ggw, k, mode, flip, transposed, tuple(gy.shape[1:3]))
+        return gx, ggy, None, None, None, None
+
+
+def conv2d(x, w, k, mode=S1, flip=False, transposed=False):
+    """x (B,H,W,Ci) NHWC, w (k*k, Co, Ci) tap-major [or (k*k, Ci, Co) with transposed=True] -> (B,Ho,Wo,Co)."""
+    hi, wi = x.shape[1:3]
+    return _Conv.apply(x, w, k, mode, flip, transposed, (conv_out_size(hi, k, mode), conv_out_size(wi, k, mode)))
+
+
+def prep_weight(weight, scale=1.0):
+    """(Co,Ci,k,k) parameter -> tap-major (k*k, Co, Ci) * scale.  Tiny tensors: plain (differentiable) torch glue."""
+    co, ci, kh, kw = weight.shape
+    return (weight * scale).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+
+
+# --------------------------------------------------------------------------------------------- upfirdn2d
+def upfirdn_out_size(h, kh, up, down, p0, p1):
+    return (h * up + p0 + p1 - kh) // down + 1
+
+
+class _UpFirDn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, up, down, py0, px0, out_hw, flip, rt):
+        x = _c(x)
+        require_cuda(x, kernel)
+        B, Hi, Wi, C = x.shape
+        kh, kw = kernel.shape
+        Ho, Wo = out_hw
+        y = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device)
+        check(lib.gifb200_upfirdn2d(ptr(x), ptr(kernel), ptr(y), B, Hi, Wi, C, Ho, Wo, kh, kw, up, down, py0, px0,
+                                    int(flip), int(rt), stream()), "gifb200_upfirdn2d")
+        ctx.kernel = kernel
+        ctx.cfg = (up, down, py0, px0, (Hi, Wi), flip, kh, kw)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        up, down, py0, px0, in_hw, flip, kh, kw = ctx.cfg
+        # adjoint: swap up/down, reverse the kernel, pad0' = k-1-pad0, output size = forward's input size
+        rt = tf32_enabled()
+        gx = _tag(_UpFirDn.apply(gy, ctx.kernel, down, up, kh - 1 - py0, kw - 1 - px0, in_hw, not flip, rt), rt)
+        return gx, None, None, None, None, None, None, None, None
+
+
+def upfirdn2d(x, kernel, up=1, down=1, pad=(0, 0), rt=False):
+    """NHWC equivalent of cl.py:42-72 (same pad on both axes, cl.py:53).  rt: round the output to tf32."""
+    kernel = _c(kernel.detach().to(torch.float32))
+    kh, kw = kernel.shape
+    ho = upfirdn_out_size(x.shape[1], kh, up, down, pad[0], pad[1])
+    wo = upfirdn_out_size(x.shape[2], kw, up, down, pad[0], pad[1])
+    return _tag(_UpFirDn.apply(x, kernel, up, down, pad[0], pad[0], (ho, wo), False, rt), rt)
+
+
+# --------------------------------------------------------------------------------------------- bias / act
+class _BiasAct(torch.autograd.Function):
+    """y = lrelu(x*rowscale[b,c] + add + bias[c], slope) * gain  (rowscale/add/bias optional)."""
+
+    @staticmethod
+    def forward(ctx, x, rowscale, add, bias, slope, gain, rt):
+        x = _c(x)
+        rowscale = None if rowscale is None else _c(rowscale)
+        add = None if add is None else _c(add)
+        bias_flat = None if bias is None else _c(bias.reshape(-1))
+        require_cuda(x, rowscale, add, bias_flat)
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // max(B * C, 1)
+        y = torch.empty_like(x)
+        check(lib.gifb200_bias_act(ptr(x), ptr(rowscale), ptr(add), ptr(bias_flat), ptr(y), B, P, C, slope, gain,
+                                   int(rt), stream()), "gifb200_bias_act")
+        ctx.save_for_backward(x, rowscale, y)
+        ctx.cfg = (slope, gain, None if bias is None else bias.shape, add is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, rowscale, y = ctx.saved_tensors
+        slope, gain, bias_shape, has_add = ctx.cfg
+        gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())   # gradient w.r.t. the pre-activation t (feeds dgrad/wgrad)
+        gx = grs = gadd = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gt if rowscale is None else chan_scale(gt, rowscale)
+        if rowscale is not None and ctx.needs_input_grad[1]:
+            grs = spatial_dot(gt, x)
+        if has_add and ctx.needs_input_grad[2]:
+            gadd = gt
+        if bias_shape is not None and ctx.needs_input_grad[3]:
+            gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
+        return gx, grs, gadd, gb, None, None, None
+
+
+class _ActBwd(torch.autograd.Function):
+    """gx = gy * gain * (y > 0 ? 1 : slope): linear in gy, piecewise constant in y."""
+
+    @staticmethod
+    def forward(ctx, gy, y, slope, gain, rt):
+        gy = _c(gy)
+        require_cuda(gy, y)
+        gx = torch.empty_like(gy)
+        check(lib.gifb200_act_bwd(ptr(gy), ptr(y), ptr(gx), gy.numel(), slope, gain, int(rt), stream()),
+              "gifb200_act_bwd")
+        ctx.save_for_backward(y)
+        ctx.cfg = (slope, gain, rt)
+        return gx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        (y,) = ctx.saved_tensors
+        slope, gain, rt = ctx.cfg
+        return _tag(_ActBwd.apply(ggx, y, slope, gain, rt), rt), None, None, None, None
+
+
+def act_bwd(gy, y, slope, gain, rt=False):
+    return _tag(_ActBwd.apply(gy, y, slope, gain, rt), rt)
+
+
+def bias_act(x, bias=None, slope=0.2, gain=math.sqrt(2.0), rowscale=None, add=None, rt=False):
+    """rt: round the output to tf32 (set when the consumer is a tensor-core convolution)."""
+    return _tag(_BiasAct.apply(x, rowscale, add, bias, float(slope), float(gain), rt), rt)
+
+
+class _RowsSum(torch.autograd.Function):
+    """(G, rows, C) -> (G, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        require_cuda(x)
+        G, rows, C = x.shape
+        out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        check(lib.gifb200_rows_sum(ptr(x), ptr(out), G, rows, C, stream()), "gifb200_rows_sum")
+        ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, None, :].expand(ctx.shape)
+
+
+def rows_sum(x):
+    return _RowsSum.apply(x)
+
+
+# --------------------------------------------------------------------------------------------- modulation
+class _ChanScale(torch.autograd.Function):
+    """y[b,...,c] = x[b,...,c] * s[b,c]."""
+
+    @staticmethod
+    def forward(ctx, x, s, round_tf32):
+        x, s = _c(x), _c(s)
+        require_cuda(x, s)
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // max(B * C, 1)
+        y = torch.empty_like(x)
+        check(lib.gifb200_chan_scale(ptr(x), ptr(s), ptr(y), B, P, C, int(round_tf32), stream()), "gifb200_chan_scale")
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        gx = chan_scale(gy, s, tf32_enabled()) if ctx.needs_input_grad[0] else None
+        gs = spatial_dot(gy, x) if ctx.needs_input_grad[1] else None
+        return gx, gs, None
+
+
+class _SpatialDot(torch.autograd.Function):
+    """out[b,c] = sum_pixels a*b."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        require_cuda(a, b)
+        B, C = a.shape[0], a.shape[-1]
+        P = a.numel() // max(B * C, 1)
+        out = torch.empty((B, C), dtype=torch.float32, device=a.device)
+        check(lib.gifb200_spatial_dot(ptr(a), ptr(b), ptr(out), B, P, C, stream()), "gifb200_spatial_dot")
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = chan_scale(b, g) if ctx.needs_input_grad[0] else None
+        gb = chan_scale(a, g) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def chan_scale(x, s, round_tf32=False):
+    return _tag(_ChanScale.apply(x, s, round_tf32), round_tf32)
+
+
+def spatial_dot(a, b):
+    return _SpatialDot.apply(a, b)
+
+
+class _Axpby(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta, rt):
+        a = _c(a)
+        b = None if b is None else _c(b)
+        require_cuda(a, b)
+        y = torch.empty_like(a)
+        check(lib.gifb200_axpby(ptr(a), ptr(b), ptr(y), a.numel(), alpha, beta, int(rt), stream()), "gifb200_axpby")
+        ctx.cfg = (alpha, beta, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, beta, has_b = ctx.cfg
+        rt = tf32_enabled()
+        ga = _tag(_Axpby.apply(g, None, alpha, 0.0, rt), rt) if ctx.needs_input_grad[0] else None
+        gb = _tag(_Axpby.apply(g, None, beta, 0.0, rt), rt) if (has_b and ctx.needs_input_grad[1]) else None
+        return ga, gb, None, None, None
+
+
+def axpby(a, b, alpha=1.0, beta=1.0, rt=False):
+    """alpha*a + beta*b on same-shape tensors."""
+    return _tag(_Axpby.apply(a, b, float(alpha), float(beta), rt), rt)
+
+
+class _Demod(torch.autograd.Function):
+    """d[b,o] = rsqrt(sum_i s[b,i]^2 q[o,i] + eps)  (cl.py:315-316).  Forward: warp-shuffle kernel; the O(B*Ci*Co)
+    backward is expressed with differentiable torch ops on these tiny matrices."""
+
+    @staticmethod
+    def forward(ctx, s, q, eps):
+        s, q = _c(s), _c(q)
+        require_cuda(s, q)
+        B, Ci = s.shape
+        Co = q.shape[0]
+        d = torch.empty((B, Co), dtype=torch.float32, device=s.device)
+        check(lib.gifb200_demod(ptr(s), ptr(q), ptr(d), B, Ci, Co, eps, stream()), "gifb200_demod")
+        ctx.save_for_backward(s, q, d)
+        return d
+
+    @staticmethod
+    def backward(ctx, gd):
+        s, q, d = ctx.saved_tensors
+        t = -0.5 * gd * d * d * d                          # d(d)/d(sum) = -1/2 d^3
+        gs = 2.0 * s * matmul(t, q) if ctx.needs_input_grad[0] else None
+        gq = matmul(t, s * s, trans_a=True) if ctx.needs_input_grad[1] else None
+        return gs, gq, None
+
+
+def demod(s, q, eps=1e-8):
+    return _Demod.apply(s, q, float(eps))
+
+
+# --------------------------------------------------------------------------------------------- ToRGB
+class _ToRgbFwd(torch.autograd.Function):
+    """y[b,p,k] = sum_i x[b,p,i] ws[b,k,i]  (k = 0..2)."""
+
+    @staticmethod
+    def forward(ctx, x, ws):
+        x, ws = _c(x), _c(ws)
+        require_cuda(x, ws)
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // max(B * C, 1)
+        y = torch.empty(x.shape[:-1] + (3,), dtype=torch.float32, device=x.device)
+        check(lib.gifb200_torgb_fwd(ptr(x), ptr(ws), ptr(y), B, P, C, stream()), "gifb200_torgb_fwd")
+        ctx.save_for_backward(x, ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, ws = ctx.saved_tensors
+        gx = _ToRgbBwdX.apply(gy, ws) if ctx.needs_input_grad[0] else None
+        gws = _ToRgbBwdW.apply(gy, x) if ctx.needs_input_grad[1] else None
+        return gx, gws
+
+
+class _ToRgbBwdX(torch.autograd.Function):
+    """gx[b,p,i] = sum_k gy[b,p,k] ws[b,k,i]."""
+
+    @staticmethod
+    def forward(ctx, gy, ws):
+        gy, ws = _c(gy), _c(ws)
+        require_cuda(gy, ws)
+        B, C = ws.shape[0], ws.shape[-1]
+        P = gy.numel() // max(B * 3, 1)
+        gx = torch.empty(gy.shape[:-1] + (C,), dtype=torch.float32, device=gy.device)
+        check(lib.gifb200_torgb_bwd_x(ptr(gy), ptr(ws), ptr(gx), B, P, C, stream()), "gifb200_torgb_bwd_x")
+        ctx.save_for_backward(gy, ws)
+        return gx
+
+    @staticmethod
+    def backward(ctx, g):
+        gy, ws = ctx.saved_tensors
+        ggy = _ToRgbFwd.apply(g, ws) if ctx.needs_input_grad[0] else None
+        gws = _ToRgbBwdW.apply(gy, g) if ctx.needs_input_grad[1] else None
+        return ggy, gws
+
+
+class _ToRgbBwdW(torch.autograd.Function):
+    """gws[b,k,i] = sum_p gy[b,p,k] x[b,p,i]."""
+
+    @staticmethod
+    def forward(ctx, gy, x):
+        gy, x = _c(gy), _c(x)
+        require_cuda(gy, x)
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // max(B * C, 1)
+        gws = torch.empty((B, 3, C), dtype=torch.float32, device=x.device)
+        check(lib.gifb200_torgb_bwd_w(ptr(gy), ptr(x), ptr(gws), B, P, C, stream()), "gifb200_torgb_bwd_w")
+        ctx.save_for_backward(gy, x)
+        return gws
+
+    @staticmethod
+    def backward(ctx, g):
+        gy, x = ctx.saved_tensors
+        ggy = _ToRgbFwd.apply(x, g) if ctx.needs_input_grad[0] else None
+        gx = _ToRgbBwdX.apply(gy, g) if ctx.needs_input_grad[1] else None
+        return ggy, gx
+
+
+def torgb(x, ws):
+    return _ToRgbFwd.apply(x, ws)
+
+
+# --------------------------------------------------------------------------------------------- small GEMM
+def _sgemm_raw(a, b, trans_a, trans_b, alpha):
+    a, b = _c(a), _c(b)
+    require_cuda(a, b)
+    M = a.shape[1] if trans_a else a.shape[0]
+    K = a.shape[0] if trans_a else a.shape[1]
+    N = b.shape[0] if trans_b else b.shape[1]
+    assert (b.shape[1] if trans_b else b.shape[0]) == K, f"sgemm inner dims {tuple(a.shape)} x {tuple(b.shape)}"
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    check(lib.gifb200_sgemm(int(trans_a), int(trans_b), M, N, K, alpha, ptr(a), a.shape[1], ptr(b), b.shape[1],
+                            ptr(c), N, stream()), "gifb200_sgemm")
+    return c
+
+
+class _MatMul(torch.autograd.Function):
+    """C = alpha * op(A) op(B)."""
+
+    @staticmethod
+    def forward(ctx, a, b, trans_a, trans_b, alpha):
+        ctx.save_for_backward(a, b)
+        ctx.cfg = (trans_a, trans_b, alpha)
+        return _sgemm_raw(a, b, trans_a, trans_b, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb, alpha = ctx.cfg
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            # C = op(A) op(B):  d/d op(A) = G op(B)^T ;  if A stored transposed: dA = (G op(B)^T)^T = op(B) G^T
+            ga = _MatMul.apply(b, g, tb, True, alpha) if ta else _MatMul.apply(g, b, False, not tb, alpha)
+        if ctx.needs_input_grad[1]:
+            # d/d op(B) = op(A)^T G ; if B stored transposed: dB = G^T op(A)
+            gb = _MatMul.apply(g, a, True, ta, alpha) if tb else _MatMul.apply(a, g, not ta, False, alpha)
+        return ga, gb, None, None, None
+
+
+def matmul(a, b, trans_a=False, trans_b=False, alpha=1.0):
+    return _MatMul.apply(a, b, trans_a, trans_b, float(alpha))
+
+
+# --------------------------------------------------------------------------------------------- cond pyramid
+class _CondDown(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, s, adjoint, full_hw):
+        x = _c(x)
+        require_cuda(x)
+        B, _, _, C = x.shape
+        H, W = full_hw
+        if not adjoint:
+            y = torch.empty((B, H // s, W // s, C), dtype=torch.float32, device=x.device)
+            check(lib.gifb200_cond_down(ptr(x), ptr(y), B, H, W, C, s, 0, stream()), "gifb200_cond_down")
+        else:
+            y = torch.empty((B, H, W, C), dtype=torch.float32, device=x.device)
+            check(lib.gifb200_cond_down(ptr(y), ptr(x), B, H, W, C, s, 1, stream()), "gifb200_cond_down(adj)")
+        ctx.cfg = (s, adjoint, full_hw)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        s, adjoint, full_hw = ctx.cfg
+        return _CondDown.apply(g, s, not adjoint, full_hw), None, None, None
+
+
+def cond_down(x, s):
+    """(B,H,W,C) -> (B,H/s,W/s,C): bilinear (align_corners=False) reduction by a power of two (gen.py:309-314)."""
+    if s == 1:
+        return x
+    return _CondDown.apply(x, s, False, tuple(x.shape[1:3]))
+
+
+# --------------------------------------------------------------------------------------------- layout helpers
+def to_nhwc(x):
+    """Reference-facing NCHW tensor -> contiguous (B,H,W,C).  Free when x is an NCHW *view* of one of our outputs."""
+    return _c(x.permute(0, 2, 3, 1))
+
+
+def to_nchw_view(x):
+    """(B,H,W,C) -> NCHW-shaped view (no copy); what the module classes return."""
+    return x.permute(0, 3, 1, 2)

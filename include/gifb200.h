@@ -1,0 +1,166 @@
+/* gifb200.h -- C ABI of libgifb200.so: the B200 (sm_100a) kernels behind GIF's StyleGAN2 / rasteriser hot path.
+ *
+ * Boundary rules:
+ *   - plain `extern "C"`, device pointers + int shapes + a `cudaStream_t` (passed as void*); no torch types;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); functions never allocate, never synchronise
+ *     the stream, never throw; return 0 on success or a negative GIFB200_E_* code, with a human readable
+ *     message available from gifb200_last_error() (thread-local);
+ *   - all activations are fp32, channels-last: x[b][y][x][c] ("NHWC"), dense.  Weights for the convolution
+ *     entry points are "tap-major": w[t][r][s] with t = kh*k + kw (see gifb200_conv2d).
+ *   - every entry point cites the reference interface it replaces (paths relative to the reference repo;
+ *     cl.py = model/stylegan2_common_layers.py).
+ *
+ * The reference has no FFI layer of its own for the StyleGAN2 ops (they are Python, cl.py:14-16 has the CUDA op
+ * imports commented out); the Python binding a maintainer adds is shown in INTEGRATION.md
+ * (gif_b200/_lib.py is that binding).  For the rasteriser the reference binding is pybind11
+ * (my_utils/standard_rasterize_cuda/standard_rasterize_cuda.cpp:79-82).
+ */
+#ifndef GIFB200_H
+#define GIFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIFB200_OK 0
+#define GIFB200_E_SHAPE (-1)     /* unsupported / inconsistent shape argument                       */
+#define GIFB200_E_ALIGN (-2)     /* pointer or channel count not aligned as the kernel requires     */
+#define GIFB200_E_ARCH (-3)      /* device is not sm_100 / driver entry point missing               */
+#define GIFB200_E_CUDA (-4)      /* CUDA runtime / driver error (message has the CUDA error string) */
+#define GIFB200_E_WORKSPACE (-5) /* workspace too small                                              */
+
+typedef void* gifb200_stream_t; /* a cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int gifb200_version(void);
+const char* gifb200_last_error(void);
+/* number of kernel launches issued through this library by the calling process since load (bench.py's
+ * "gpu_launches" is the difference of this counter across the timed region) */
+long long gifb200_launch_count(void);
+
+/* ---- convolution (dense 3x3 / 1x1 contraction) -------------------------------------------------------
+ * Replaces: F.conv2d / F.conv_transpose2d inside ModulatedConv2d.forward (cl.py:307-349, in the
+ * modulate-input / shared-weight form of SURVEY A3), EqualConv2d.forward (cl.py:175-184), the three
+ * nn.Conv2d of NoiseInjection (cl.py:405-414) and their autograd (backward + double backward).
+ *
+ *   mode 0 (S1): stride 1, zero pad k/2        y[b,yo,xo,o] = sum_{t,i} x[b, yo+kh-k/2, xo+kw-k/2, i] * W[t,o,i]
+ *   mode 1 (S2): stride 2, no pad              y[b,yo,xo,o] = sum_{t,i} x[b, 2yo+kh, 2xo+kw, i]     * W[t,o,i]
+ *                (Hi >= 2*Ho + k - 2; D's downsampling convs, cl.py:765-786)
+ *   mode 2 (T2): transposed stride 2, no pad   y[b,Y,X,o]   = sum_{t,i: Y-kh, X-kw even} x[b,(Y-kh)/2,(X-kw)/2,i] * W[t,o,i]
+ *                (Ho = 2*Hi + k - 2; G's upsampling modconv, cl.py:322-331)
+ *
+ * Logical weights W[t,o,i] are addressed inside the physical buffer w[T][R][S] (T = k*k):
+ *     tt = flip ? T-1-t : t;   W[t,o,i] = transposed ? w[tt][i][o] (R = Ci, S = Co) : w[tt][o][i] (R = Co, S = Ci)
+ * so that the adjoint (input-gradient) of every mode is another call on the SAME weight buffer:
+ *     adj(S1, flip, tr) = (S1, !flip, !tr);  adj(S2, flip, tr) = (T2, flip, !tr);  adj(T2, flip, tr) = (S2, flip, !tr).
+ *
+ * impl: 0 = auto (tcgen05 tensor-core path when the shape qualifies, else SIMT), 1 = force SIMT fp32,
+ *       2 = force tcgen05 (kind::tf32, fp32 accumulate; returns GIFB200_E_SHAPE if the shape does not qualify).
+ * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL). */
+size_t gifb200_conv2d_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
+                                      int transposed, int impl);
+int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
+                   int k, int mode, int flip, int transposed, int impl, void* workspace, size_t workspace_bytes,
+                   gifb200_stream_t stream);
+
+/* Weight gradient of gifb200_conv2d for the same (mode, flip, transposed), written in the PHYSICAL layout of w
+ * (so it can be accumulated into / compared with the weight buffer directly):
+ *     gW[t,o,i] = sum_{b,pixels} gy[b,p_out,o] * x[b,p_in(p_out,t),i]   (p_in as in the mode's formula above)
+ * x is the conv input (B,Hi,Wi,Ci), gy the conv output gradient (B,Ho,Wo,Co).  gw is OVERWRITTEN.
+ * Replaces autograd's conv weight gradient for the reference modules listed above. */
+size_t gifb200_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
+                                            int impl);
+int gifb200_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
+                         int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,
+                         size_t workspace_bytes, gifb200_stream_t stream);
+
+/* ---- upfirdn2d ---------------------------------------------------------------------------------------
+ * Replaces upfirdn2d (cl.py:42-72) and through it Blur (cl.py:136-152), Upsample (cl.py:94-112),
+ * Downsample (cl.py:115-133); its adjoint is the same entry point:
+ *     out[b,y,x,c] = sum_{a,b'} K[a,b'] * U[y*down + (kh-1-a) - pad_y0, x*down + (kw-1-b') - pad_x0]
+ * with U = input with (up-1) zeros inserted after every sample, zero outside; K = flip ? kernel reversed in
+ * both axes : kernel.  Negative pads crop.  The output size (Ho,Wo) is given by the caller
+ * (forward: (H*up + pad0 + pad1 - kh)/down + 1; adjoint: the forward's input size).
+ * kernel: kh*kw floats on the device, kh,kw <= 8.  C % 4 == 0 takes the vectorised path. */
+int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, int B, int Hi, int Wi, int C, int Ho, int Wo,
+                      int kh, int kw, int up, int down, int pad_y0, int pad_x0, int flip, int round_tf32,
+                      gifb200_stream_t stream);
+
+/* ---- fused bias / demodulation / noise-add / leaky-ReLU -----------------------------------------------
+ * Replaces FusedLeakyReLU.forward (cl.py:32-39), the tail of StyledConv.forward (cl.py:479-486: demodulate,
+ * NoiseInjection add, bias, activation), ScaledLeakyReLU (cl.py:238-247) and plain bias adds:
+ *     t = x[b,p,c] * rowscale[b,c] + add[b,p,c] + bias[c];   y = (t > 0 ? t : slope*t) * gain
+ * rowscale, add, bias may each be NULL.  rows = B*P pixels in total, P pixels per sample.
+ * round_tf32 (here and below): != 0 rounds the OUTPUT to tf32 (round-to-nearest-away, cvt.rna) -- set by the caller
+ * when the consumer is a tcgen05 kind::tf32 contraction, which truncates its operands: pre-rounded operands make
+ * that truncation exact and the contraction unbiased. */
+int gifb200_bias_act(const float* x, const float* rowscale, const float* add, const float* bias, float* y, int B,
+                     int P, int C, float slope, float gain, int round_tf32, gifb200_stream_t stream);
+/* Backward of the activation given the OUTPUT y:  gx = gy * gain * (y > 0 ? 1 : slope)  (second derivative is
+ * zero a.e., so this is also its own double-backward rule). n = number of elements. */
+int gifb200_act_bwd(const float* gy, const float* y, float* gx, long long n, float slope, float gain,
+                    int round_tf32, gifb200_stream_t stream);
+/* out[g,c] = sum_{r<rows} x[g,r,c]  (bias gradients: G = 1; per-sample reductions: G = B). out is OVERWRITTEN. */
+int gifb200_rows_sum(const float* x, float* out, int G, int rows, int C, gifb200_stream_t stream);
+/* y[b,p,c] = x[b,p,c] * s[b,c]  -- style modulation of the conv INPUT (cl.py:311-312 moved to the activation),
+ * demodulation of the conv OUTPUT (cl.py:315-316).  round_tf32 != 0 rounds y to tf32 (round-to-nearest) so that
+ * the tcgen05 kind::tf32 contraction, which truncates, sees exactly representable operands. */
+int gifb200_chan_scale(const float* x, const float* s, float* y, int B, int P, int C, int round_tf32,
+                       gifb200_stream_t stream);
+/* out[b,c] = sum_p a[b,p,c] * b2[b,p,c]  (gradient of chan_scale w.r.t. s). out is OVERWRITTEN. */
+int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream);
+/* y = alpha*a + beta*b (b may be NULL): residual merge (a+b)/sqrt2 of ResBlock.forward (cl.py:817-818),
+ * skip accumulation of ToRGB (cl.py:509), noise add. */
+int gifb200_axpby(const float* a, const float* b, float* y, long long n, float alpha, float beta, int round_tf32,
+                  gifb200_stream_t stream);
+/* d[b,o] = rsqrt(sum_i s[b,i]^2 * q[o,i] + eps): style-vector demodulation coefficients (cl.py:315; q[o,i] =
+ * sum_taps W~[o,i,.,.]^2), one warp per (b,o) with a shuffle reduction. */
+int gifb200_demod(const float* s, const float* q, float* d, int B, int Ci, int Co, float eps, gifb200_stream_t stream);
+
+/* ---- ToRGB: per-sample 1x1 convolution to 3 channels (no demodulation) ----------------------------------
+ * Replaces ToRGB.forward's ModulatedConv2d(k=1, demodulate=False) (cl.py:498-504). ws[b,3,C] = W~rgb[c3,i]*s[b,i]
+ * is computed by the caller (tiny).  y[b,p,3] = sum_i x[b,p,i] * ws[b,:,i]. */
+int gifb200_torgb_fwd(const float* x, const float* ws, float* y, int B, int P, int C, gifb200_stream_t stream);
+int gifb200_torgb_bwd_x(const float* gy, const float* ws, float* gx, int B, int P, int C, gifb200_stream_t stream);
+int gifb200_torgb_bwd_w(const float* gy, const float* x, float* gws, int B, int P, int C, gifb200_stream_t stream);
+
+/* ---- small dense GEMM (EqualLinear) -------------------------------------------------------------------
+ * Replaces F.linear in EqualLinear.forward (cl.py:212-230) and its gradients. Row-major:
+ *     C[M,N] = alpha * op(A) * op(B),  op(A) is M x K (A stored K x M if transA), op(B) is K x N (N x K if transB). */
+int gifb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                  int ldb, float* C, int ldc, gifb200_stream_t stream);
+
+/* ---- condition pyramid ----------------------------------------------------------------------------------
+ * Replaces F.interpolate(cond, (r,r), 'bilinear', align_corners=False) for power-of-two reductions
+ * (stg2_generator.py:309-314; SURVEY A2: mean of the central 2x2 of each s x s block). x (B,H,W,C) -> y (B,H/s,W/s,C).
+ * adjoint != 0 computes the transpose map (y given, x produced, zeros elsewhere). */
+int gifb200_cond_down(float* x, float* y, int B, int H, int W, int C, int s, int adjoint,
+                      gifb200_stream_t stream);
+
+/* ---- rasteriser ---------------------------------------------------------------------------------------
+ * Replaces standard_rasterize / standard_rasterize_colors
+ * (my_utils/standard_rasterize_cuda/standard_rasterize_cuda.cpp:26-40,59-75; kernels
+ * standard_rasterize_cuda_kernel.cu:112-233).  Same contract: face_vertices (B,F,3,3) fp32 in pixel space,
+ * caller-initialised depth (B,h,w) / triangle (B,h,w) int32 / bary-or-image (B,h,w,3) buffers updated IN PLACE.
+ * Deterministic: exact depth ties are won by the lowest face index; fp32 arithmetic is evaluated without FMA
+ * contraction (bit-exact against oracle/rasterize_oracle.c).  face_colors == NULL selects standard_rasterize
+ * (out3 = barycentric weights), otherwise standard_rasterize_colors (out3 = interpolated colours). */
+size_t gifb200_rasterize_workspace_bytes(int B, int F, int h, int w);
+int gifb200_rasterize_fwd(const float* face_vertices, const float* face_colors, float* depth, int32_t* triangle,
+                          float* out3, int B, int F, int h, int w, void* workspace, size_t workspace_bytes,
+                          gifb200_stream_t stream);
+/* Backward (absent in the reference): given the forward's triangle buffer and upstream gradients of the
+ * barycentric weights g_bary (B,h,w,3) and/or interpolated colours g_img (B,h,w,3) and/or depth g_depth (B,h,w)
+ * (each may be NULL), accumulates into g_face_vertices (B,F,3,3) and g_face_colors (B,F,3,3) (may be NULL).
+ * Both gradient outputs must be zero-initialised by the caller (scatter-add). */
+int gifb200_rasterize_bwd(const float* face_vertices, const float* face_colors, const int32_t* triangle,
+                          const float* g_bary, const float* g_img, const float* g_depth, float* g_face_vertices,
+                          float* g_face_colors, int B, int F, int h, int w, gifb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIFB200_H */
