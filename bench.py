@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- G+D training-step throughput (images/sec) at 256^2, batch 32 per GPU: BASELINE.json's metric on
+configs[2] ("full G+D train step (R1 + path-length reg) 256x256 bs32, synthetic FFHQ + FLAME, 1xB200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-ppl]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one full iteration of the reference's loop body (train.py:80-252): D step
+(real + fake forward, backward, Adam) + G step (G and D forward, backward, Adam, EMA), with the R1 penalty every 16th
+iteration (train.py:145) and the path-length regulariser (adopted rule, PARITY UNPINNED) every iteration unless --no-ppl.
+Inputs are synthetic FFHQ-shaped images U(-1,1), synthetic FLAME-render-shaped conditions U(-1,1), random identity indices;
+weights are random-initialised as the reference's constructors do.
+
+  value        images/sec, whole job, inputs resident in HBM, CUDA-event timed, max over ranks.
+  e2e          same loop, but every step copies that step's inputs from PINNED HOST memory and reads the two loss
+               scalars back (the call a user of train.py makes: host batch in, losses out).
+  roofline     the dominant kernel = the tcgen05 implicit-GEMM convolution (conv_tc_kernel): algorithmic FLOPs of
+               every launch inside the timed region / its CUDA-event duration, against the tf32 tensor peak
+               (= half of MEASURED_PEAKS.json's sustained bf16 figure -- the file has no tf32 entry).
+  cpu_baseline the oracle port of the reference (oracle/stylegan2_oracle.py, torch CPU, all host threads) on a
+               bounded sample: ONE iteration at batch 1 without R1/PPL (~10-30 s).
+  --impl reference   times only that CPU arm (the reference is Python and cannot travel to the GPU box; the port is
+               pinned to it at 1e-15 in fp64, tests/golden/ORACLE_VS_REFERENCE.txt).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "G+D train step images/sec @256x256 bs32/GPU"
+RES, BATCH, VOCAB = 256, 32, 70_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gif_b200", choices=["gif_b200", "reference"])
+    ap.add_argument("--no-ppl", action="store_true", help="drop the path-length regulariser from the G step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(steps, warmup):
+    """The oracle port on the host cores: one D+G iteration at batch 1, 256^2 (no R1 / PPL) per step."""
+    import golden_util as gu
+    from oracle import stylegan2_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sdg = gu.seeded_state_dict(gu.g_shapes(100), 1)
+    sdd = gu.seeded_state_dict(gu.d_shapes(RES), 3)
+    gp = [k for k in sdg if "kernel" not in k and "embd" not in k]
+    dp = [k for k in sdd if "kernel" not in k]
+    for k in gp:
+        sdg[k].requires_grad_(True)
+    for k in dp:
+        sdd[k].requires_grad_(True)
+    b = 1
+    cond, real, idx = gu.rand_uniform((b, 6, RES, RES), 1), gu.rand_uniform((b, 3, RES, RES), 2), gu.randint(100, (b,), 3)
+
+    def one():
+        with torch.no_grad():
+            fake = O.generator_forward(cond, idx, sdg, 6)
+        loss = O.d_logistic_loss(O.discriminator_forward(real, cond, sdd, RES), O.discriminator_forward(fake, cond, sdd, RES))
+        torch.autograd.grad(loss, [sdd[k] for k in dp])
+        fake = O.generator_forward(cond, idx, sdg, 6)
+        gl = O.g_nonsat_loss(O.discriminator_forward(fake, cond, sdd, RES))
+        torch.autograd.grad(gl, [sdg[k] for k in gp], allow_unused=True)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": b / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"{steps} iteration(s) of the D+G step at batch {b}, 256x256, no R1/PPL, oracle/stylegan2_oracle.py "
+                      f"(torch CPU fp32, {cores} threads), {dt:.1f} s per iteration"}
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 2))
+    cb = cpu_arm(steps, 1 if args.warmup > 0 else 0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": 1000.0 / cb["value"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train_step_256_bs32 (CPU arm: bounded sample at batch 1, see cpu_baseline.sample)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_main(args)
+    from gif_b200 import _lib, ops
+    from gif_b200.distributed import broadcast_module, init_from_env
+    from gif_b200.train_step import GifTrainer
+    import torch.distributed as dist
+
+    rank, world, local = init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    ops.set_precision("tf32")
+    B = args.batch
+    trainer = GifTrainer(dev, RES, VOCAB, r1_every=16, ppl=not args.no_ppl, world_size=world, seed=0)
+    broadcast_module(trainer.generator)
+    broadcast_module(trainer.discriminator)
+    trainer.g_running.load_state_dict(trainer.generator.state_dict())
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4   # distinct pinned host batches cycled through (each 75.5 MB)
+    host = [(torch.rand(B, 3, RES, RES, generator=gen).mul_(2).sub_(1).pin_memory(),
+             torch.rand(B, 6, RES, RES, generator=gen).mul_(2).sub_(1).pin_memory(),
+             torch.randint(0, VOCAB, (B,), generator=gen).pin_memory()) for _ in range(n_host)]
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    # R1 must fall inside every timed window: start the iteration counter so that the window contains
+    # ceil(K/16) penalty iterations, the same share as in the reference's loop.
+    def run(n, e2e):
+        out = None
+        for s in range(n):
+            if e2e:
+                hb = host[s % n_host]
+                real, cond, idx = (t.to(dev, non_blocking=True) for t in hb)
+            else:
+                real, cond, idx = resident[s % n_host]
+            out = trainer.train_iteration(real, cond, idx)
+            if e2e:
+                out = (out[0].item(), out[1].item())      # device -> host read of the step's result
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        trainer.iteration = 16 - 1 - (n - 1) % 16 if n < 16 else 0      # the last iteration of a short window is an R1 one
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(n, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # warm-up (also includes one R1 iteration so that every kernel variant is loaded)
+    trainer.iteration = 16 - args.warmup
+    run(args.warmup, False)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ops.PROFILE = [] if rank == 0 else None
+    ms = timed(args.steps, False)
+    launches = _lib.launch_count() - launches0
+    prof = ops.PROFILE
+    ops.PROFILE = None
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e = timed(args.steps, True)
+        e2e = {"value": world * B * args.steps / (ms_e / 1000.0), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 8}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel from the per-launch CUDA events recorded inside the timed region
+    roof = None
+    if prof:
+        torch.cuda.synchronize()
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+        tot_fl = sum(f for _, _, f, _ in prof)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        bf16 = peaks.get("bf16_tflops_sustained")
+        peak = bf16 / 2 if bf16 else 1400.0 / 2
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        ns = [(a.elapsed_time(b), f) for a, b, f, tag in prof if tag == "northstar"]
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate; no tf32 entry"
+                                " in the file)") if bf16 else "fallback 1.4 PFLOP/s sustained bf16 / 2",
+                "launches": len(prof), "kernel_ms_per_step": tot_ms / args.steps,
+                "share_of_step": tot_ms / ms,
+                "northstar_layer_tflops": (sum(f for _, f in ns) / (sum(t for t, _ in ns) * 1e-3) / 1e12) if ns else None}
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_arm(1, 0)
+    line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 tensor-core contraction, f32 accumulate/storage", "data": "synthetic",
+            "config": {"workload": "train_step_256_bs32: StyledGenerator(70000 ids) + Discriminator(256, 9ch), D step + G step, "
+                                   "Adam, EMA, R1 every 16th iteration" + ("" if args.no_ppl else ", path-length reg every iteration"),
+                       "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,8 +10,24 @@ namespace gifb200 {
 
 struct ConvParams {
     int B, Hi, Wi, Ci, Ho, Wo, Co, k, flip;
-    long long M;  // B*Ho*Wo
+    long long M;  // number of output pixels this launch produces (B*Ho*Wo, or B*(Wo+Ho-1) in strip mode)
+    int strip;    // 1: only the last output row and the last output column (border strip of a T2 convolution)
 };
+
+// m-th output pixel of the launch -> (b, yo, xo)
+__device__ __forceinline__ void decode_pixel(const ConvParams& p, long long m, int& b, int& yo, int& xo) {
+    if (!p.strip) {
+        xo = static_cast<int>(m % p.Wo);
+        const long long r = m / p.Wo;
+        yo = static_cast<int>(r % p.Ho);
+        b = static_cast<int>(r / p.Ho);
+    } else {
+        const int per = p.Wo + p.Ho - 1;
+        b = static_cast<int>(m / per);
+        const int idx = static_cast<int>(m % per);
+        if (idx < p.Wo) { yo = p.Ho - 1; xo = idx; } else { xo = p.Wo - 1; yo = idx - p.Wo; }
+    }
+}
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
@@ -48,12 +64,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
     const long long a_m = m0 + a_row;
     int a_b = 0, a_yo = 0, a_xo = 0;
     const bool a_ok = a_m < p.M;
-    if (a_ok) {
-        a_xo = static_cast<int>(a_m % p.Wo);
-        const long long r = a_m / p.Wo;
-        a_yo = static_cast<int>(r % p.Ho);
-        a_b = static_cast<int>(r / p.Ho);
-    }
+    if (a_ok) decode_pixel(p, a_m, a_b, a_yo, a_xo);
     const int tm = (tid >> 4) << 2, tn = (tid & 15) << 2;
     float acc[4][4];
 #pragma unroll
@@ -109,10 +120,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
     for (int i = 0; i < 4; ++i) {
         const long long m = m0 + tm + i;
         if (m >= p.M) continue;
+        int ob, oy, ox;
+        decode_pixel(p, m, ob, oy, ox);
+        float* yrow = y + ((static_cast<long long>(ob) * p.Ho + oy) * p.Wo + ox) * p.Co;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int o = n0 + tn + j;
-            if (o < p.Co) y[m * p.Co + o] = acc[i][j];
+            if (o < p.Co) yrow[o] = acc[i][j];
         }
     }
 }
@@ -207,12 +221,27 @@ static int check_conv_shape(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int C
     return GIFB200_OK;
 }
 
+static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
+                            int Co, int k, int mode, int flip, int transposed, int strip, cudaStream_t st);
+
 int conv2d_simt(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
                 int mode, int flip, int transposed, cudaStream_t st) {
+    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, 0, st);
+}
+
+// last output row + last output column of a T2 convolution (the part the tcgen05 phase kernels do not cover)
+int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
+                      int k, int flip, int transposed, cudaStream_t st) {
+    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, 2, flip, transposed, 1, st);
+}
+
+static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
+                            int Co, int k, int mode, int flip, int transposed, int strip, cudaStream_t st) {
     int rc = check_conv_shape(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (rc != GIFB200_OK) return rc;
     if (B == 0) return GIFB200_OK;
-    ConvParams p{B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, static_cast<long long>(B) * Ho * Wo};
+    ConvParams p{B, Hi, Wi, Ci, Ho, Wo, Co, k, flip,
+                 strip ? static_cast<long long>(B) * (Wo + Ho - 1) : static_cast<long long>(B) * Ho * Wo, strip};
     const long long mb = (p.M + BM - 1) / BM;
     GIFB200_REQUIRE(mb <= 2147483647LL && cdiv(Co, BN) <= 65535, GIFB200_E_SHAPE, "conv2d: grid too large");
     dim3 grid(static_cast<unsigned>(mb), cdiv(Co, BN));

@@ -1,10 +1,344 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands: nothing qualifies).
-#include "common.cuh"
+// tcgen05 implicit-GEMM convolution for sm_100a (kind::tf32, fp32 accumulation in TMEM).
+//
+// GEMM view (per output "phase"):  D[site, o] = sum_{tap} sum_{i} A_tap[site, i] * W[tap][o][i]
+//   M = 128 sites per CTA (a wt x ht x nt box of the site grid (B, Hs, Ws)), N = BLOCK_N output channels,
+//   K = 32 input channels per pipeline stage (one 128-byte swizzle row of fp32), taps x Ci/32 stages per tile.
+//   * A operand: the activation tensor itself (channels-last fp32) -- no im2col buffer.  Each tap is the same TMA box
+//     shifted by the tap offset; TMA's out-of-bounds zero fill implements the padding.  Stride-2 convolutions (S2)
+//     read through a 5-D view that splits W into (parity, W/2) and load one site row per TMA issue; transposed
+//     stride-2 convolutions (T2) run as 4 output phases (Y%2, X%2), each an ordinary stride-1 gather with its own
+//     subset of the 9 taps, and write with output stride 2.
+//   * B operand: the tap-major weights [T][Co][Ci] staged once per call into the workspace (honouring flip /
+//     transposed, rounded to tf32), K-major, 128B swizzle.
+//   * Both operands are K-major SWIZZLE_128B; one tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BLOCK_N, K=8) per
+//     32-byte K slice, issued by one thread; accumulators live in TMEM (BLOCK_N columns).
+//   * Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
+//     (tcgen05.ld 32x32b -> registers -> 16-byte global stores, channels-last).
+//   * 3-stage smem ring (96 KB) so that two CTAs share an SM: one CTA's epilogue overlaps the other's main loop.
+//
+// Operand precision: kind::tf32 reads the upper 19 bits of each fp32 (truncation).  Callers hand in activations that
+// are already rounded to tf32 (gif_b200.ops rounds in the producing kernel), weights are rounded here, so the
+// truncation is exact and the contraction is an unbiased tf32 x tf32 -> fp32 product sum.
+#include "tc_common.cuh"
+
 namespace gifb200 {
-bool conv2d_tc_supported(int, int, int, int, int, int, int, int, int) { return false; }
-size_t conv2d_tc_workspace_bytes(int, int, int, int, int, int, int, int, int, int) { return 0; }
-int conv2d_tc(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, void*, size_t,
-              cudaStream_t) {
-    return fail(GIFB200_E_SHAPE, "conv2d_tc: not built");
+
+int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
+                      int k, int flip, int transposed, cudaStream_t st);
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                         // fp32 elements = 128 bytes = one swizzle row
+constexpr int kATileBytes = kBlockM * kBlockK * 4;  // 16 KB
+constexpr int kMaxTaps = 9;
+
+struct TcParams {
+    int B, Hs, Ws;          // site grid per image
+    int wt, ht, nt;         // tile box (wt*ht*nt == 128)
+    int tiles_x, tiles_y;   // tiles per image group
+    int Ci, Co;
+    int s2;                 // 1: A loads go through the 5-D parity view, one site row per TMA issue
+    int Ho, Wo;             // output tensor spatial size
+    int oys, oxs;           // output pixel = site * o?s + o?0
+    int nphase;
+    int phase_oy0[4], phase_ox0[4], phase_ntaps[4];
+    int tap_w[4][kMaxTaps];     // weight tap index (into the staged [T][Co][Ci] buffer)
+    int tap_dy[4][kMaxTaps];    // input row    = site_y * in_sy + tap_dy
+    int tap_dx[4][kMaxTaps];    // input column = site_x + tap_dx        (S2: column in the W/2 space)
+    int tap_par[4][kMaxTaps];   // S2: W parity plane
+    int in_sy;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+    static constexpr int kBTileBytes = BLOCK_N * kBlockK * 4;
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kBarrierOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarrierOffset + 128;   // full[3], empty[3], tmem_full, tmem ptr
+    static constexpr int kDynamic = kTotal + 1024;        // slack for manual 1024 B alignment
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                         const __grid_constant__ CUtensorMap map_b,
+                                                         float* __restrict__ y, const TcParams p) {
+    using L = SmemLayout<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile coordinates
+    const int phase = blockIdx.z;
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int n0 = tile * p.nt, y0 = ty * p.ht, x0 = tx * p.wt;
+    const int nblk = blockIdx.y;
+    const int ntaps = p.phase_ntaps[phase];
+    const int kchunks = p.Ci / kBlockK;
+    const int iters = ntaps * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BLOCK_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int tap = it / kchunks, c0 = (it % kchunks) * kBlockK;
+            mbar_wait(&empty_bar[stage], ph ^ 1);
+            uint8_t* a_dst = smem + stage * L::kStageBytes;
+            uint8_t* b_dst = a_dst + kATileBytes;
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            const int dy = p.tap_dy[phase][tap], dx = p.tap_dx[phase][tap];
+            if (!p.s2) {
+                tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+            } else {
+                const int par = p.tap_par[phase][tap];
+                const int row_bytes = p.wt * kBlockK * 4;
+                for (int n = 0; n < p.nt; ++n)
+                    for (int h = 0; h < p.ht; ++h)
+                        tma_load_5d(a_dst + (n * p.ht + h) * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
+                                    (y0 + h) * p.in_sy + dy, n0 + n);
+            }
+            tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+            if (++stage == kStages) { stage = 0; ph ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_tf32(kBlockM, BLOCK_N);
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(&full_bar[stage], ph);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+            const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+            const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
+                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+            if (++stage == kStages) { stage = 0; ph ^= 1; }
+        }
+        umma_commit(tmem_full_bar);                  // accumulator complete
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp - 4;                      // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                 // tile row == TMEM lane
+        const int w_in = r % p.wt, h_in = (r / p.wt) % p.ht, n_in = r / (p.wt * p.ht);
+        const int n = n0 + n_in;
+        const int Y = (y0 + h_in) * p.oys + p.phase_oy0[phase], X = (x0 + w_in) * p.oxs + p.phase_ox0[phase];
+        const bool ok = n < p.B && Y < p.Ho && X < p.Wo;
+        float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + c + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BLOCK_N) : "memory");
+    }
 }
+
+// stage logical weights W[t][o][i] (from the physical buffer + flip/transposed) as [T][Co][Ci], rounded to tf32
+__global__ void __launch_bounds__(256) stage_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int T,
+                                                            int Co, int Ci, int flip, int transposed) {
+    const long long total = static_cast<long long>(T) * Co * Ci;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int i = static_cast<int>(e % Ci);
+        const int o = static_cast<int>((e / Ci) % Co);
+        const int t = static_cast<int>(e / (static_cast<long long>(Ci) * Co));
+        const int tt = flip ? T - 1 - t : t;
+        const float v = transposed ? w[(static_cast<long long>(tt) * Ci + i) * Co + o]
+                                   : w[(static_cast<long long>(tt) * Co + o) * Ci + i];
+        out[e] = round_tf32(v);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int pick_block_n(int Co) {
+    if (Co % 128 == 0) return 128;
+    if (Co % 64 == 0) return 64;
+    if (Co % 32 == 0) return 32;
+    return 0;
+}
+
+void site_grid(int Hi, int Wi, int Ho, int Wo, int mode, int& Hs, int& Ws) {
+    if (mode == 2) { Hs = Hi; Ws = Wi; } else { Hs = Ho; Ws = Wo; }
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* y, const TcParams& p, int mtiles, cudaStream_t st) {
+    using L = SmemLayout<BLOCK_N>;
+    static bool attr_set = false;   // per-process, idempotent
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(conv_tc_kernel)", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid(mtiles, p.Co / BLOCK_N, p.nphase);
+    conv_tc_kernel<BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ma, mb, y, p);
+    GIFB200_LAUNCH_CHECK("conv_tc_kernel");
+    return GIFB200_OK;
+}
+
+}  // namespace
+
+bool conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode) {
+    if (B <= 0 || Ci % 32 != 0 || pick_block_n(Co) == 0) return false;
+    if (!(k == 3 || (k == 1 && mode == 0))) return false;
+    if (mode == 0 && !(Ho == Hi && Wo == Wi)) return false;
+    if (mode == 1 && !(Hi == 2 * Ho + 1 && Wi == 2 * Wo + 1)) return false;
+    if (mode == 2 && !(Ho == 2 * Hi + 1 && Wo == 2 * Wi + 1)) return false;
+    int Hs, Ws;
+    site_grid(Hi, Wi, Ho, Wo, mode, Hs, Ws);
+    if (!pow2(Hs) || !pow2(Ws) || Ws < 4 || Hs < 4 || Ws > 4096 || Hs > 4096) return false;
+    return true;
+}
+
+size_t conv2d_tc_workspace_bytes(int, int, int, int Ci, int, int, int Co, int k, int, int) {
+    return static_cast<size_t>(k) * k * Co * Ci * sizeof(float) + 256;
+}
+
+int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
+              int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GIFB200_REQUIRE(conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE, "conv2d_tc: unsupported shape");
+    GIFB200_REQUIRE(ws && ws_bytes >= conv2d_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, transposed),
+                    GIFB200_E_WORKSPACE, "conv2d_tc: workspace too small (see gifb200_conv2d_workspace_bytes)");
+    GIFB200_REQUIRE(aligned16(x) && aligned16(y), GIFB200_E_ALIGN, "conv2d_tc: x / y must be 16-byte aligned");
+    const int T = k * k;
+    float* wst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+    {
+        const long long total = static_cast<long long>(T) * Co * Ci;
+        int blocks = cdiv(total, 256 * 4);
+        if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+        stage_weights_kernel<<<blocks, 256, 0, st>>>(w, wst, T, Co, Ci, flip, transposed);
+        GIFB200_LAUNCH_CHECK("stage_weights_kernel");
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Ci = Ci; p.Co = Co; p.Ho = Ho; p.Wo = Wo;
+    site_grid(Hi, Wi, Ho, Wo, mode, p.Hs, p.Ws);
+    p.wt = p.Ws < 128 ? p.Ws : 128;
+    p.ht = (128 / p.wt) < p.Hs ? (128 / p.wt) : p.Hs;
+    p.nt = 128 / (p.wt * p.ht);
+    p.tiles_x = p.Ws / p.wt; p.tiles_y = p.Hs / p.ht;
+    const int tiles_n = (B + p.nt - 1) / p.nt;
+    const long long mtiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_n;
+    GIFB200_REQUIRE(mtiles <= 2147483647LL, GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
+    p.s2 = mode == 1;
+    p.in_sy = mode == 1 ? 2 : 1;
+    const int pad = k / 2;
+    if (mode == 0) {
+        p.nphase = 1; p.oys = p.oxs = 1; p.phase_ntaps[0] = T;
+        for (int t = 0; t < T; ++t) { p.tap_w[0][t] = t; p.tap_dy[0][t] = t / k - pad; p.tap_dx[0][t] = t % k - pad; }
+    } else if (mode == 1) {
+        p.nphase = 1; p.oys = p.oxs = 1; p.phase_ntaps[0] = T;
+        for (int t = 0; t < T; ++t) {
+            const int kh = t / k, kw = t % k;
+            p.tap_w[0][t] = t; p.tap_dy[0][t] = kh; p.tap_dx[0][t] = kw >> 1; p.tap_par[0][t] = kw & 1;
+        }
+    } else {
+        // output (Y,X) = (2y+py, 2x+px), y<Hi, x<Wi; taps with kh%2==py, kw%2==px read input (y+(py-kh)/2, x+(px-kw)/2).
+        // Row Y=2Hi and column X=2Wi are produced by the SIMT strip kernel below.
+        p.nphase = 4; p.oys = p.oxs = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            const int py = ph >> 1, px = ph & 1;
+            p.phase_oy0[ph] = py; p.phase_ox0[ph] = px;
+            int n = 0;
+            for (int kh = py; kh < 3; kh += 2)
+                for (int kw = px; kw < 3; kw += 2) {
+                    p.tap_w[ph][n] = kh * 3 + kw; p.tap_dy[ph][n] = (py - kh) / 2; p.tap_dx[ph][n] = (px - kw) / 2;
+                    ++n;
+                }
+            p.phase_ntaps[ph] = n;
+        }
+    }
+    // ---- tensor maps
+    CUtensorMap ma, mb;
+    int rc;
+    if (mode != 1) {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(Wi), static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Wi) * Ci * 4,
+                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p.wt), static_cast<cuuint32_t>(p.ht), static_cast<cuuint32_t>(p.nt)};
+        rc = encode_map(&ma, x, 4, dims, strides, box);
+    } else {
+        // (C, parity, ceil(W/2), H, N): column 2*j + par of row h.  The (par=1, j=W/2) element of an odd-width row lies in
+        // the next row; it is never addressed (max column read is 2*(Wo-1)+2 = Wi-1).
+        const cuuint64_t dims[5] = {static_cast<cuuint64_t>(Ci), 2, static_cast<cuuint64_t>((Wi + 1) / 2), static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Ci) * 8,
+                                       static_cast<cuuint64_t>(Wi) * Ci * 4, static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint32_t box[5] = {kBlockK, 1, static_cast<cuuint32_t>(p.wt), 1, 1};
+        rc = encode_map(&ma, x, 5, dims, strides, box);
+    }
+    if (rc != GIFB200_OK) return rc;
+    const int bn = pick_block_n(Co);
+    {
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(Co), static_cast<cuuint64_t>(T)};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Co) * Ci * 4};
+        const cuuint32_t box[3] = {kBlockK, static_cast<cuuint32_t>(bn), 1};
+        rc = encode_map(&mb, wst, 3, dims, strides, box);
+        if (rc != GIFB200_OK) return rc;
+    }
+    if (bn == 128) rc = launch<128>(ma, mb, y, p, static_cast<int>(mtiles), st);
+    else if (bn == 64) rc = launch<64>(ma, mb, y, p, static_cast<int>(mtiles), st);
+    else rc = launch<32>(ma, mb, y, p, static_cast<int>(mtiles), st);
+    if (rc != GIFB200_OK) return rc;
+    if (mode == 2)   // last output row / column of the transposed convolution (exact fp32 SIMT, ~1/128 of the pixels)
+        return conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, st);
+    return GIFB200_OK;
+}
+
 }  // namespace gifb200

@@ -1,0 +1,295 @@
+// tcgen05 weight-gradient kernel (kind::tf32): R[t][cs][cb] = sum_{pixels p} S[p][cs] * Bg[map(p,t)][cb]
+//
+//   S  = "small-grid" tensor (B,Hs,Ws,Cs): the conv OUTPUT gradient for S1/S2, the conv INPUT for T2
+//   Bg = "big" tensor (B,Hb,Wb,Cb) read at map(p,t) = (y+kh-pad, x+kw-pad)  (S1)  or (2y+kh, 2x+kw)  (S2 / T2)
+//
+// GEMM view per CTA: M = 128 small channels, N = BLOCK_N big channels, K = pixels.  Both operands are
+// channels-last, i.e. MN-contiguous ("MN-major"): a TMA box (32 channels x P pixels) lands as P rows of 128 bytes,
+// which is exactly the canonical MN-major SWIZZLE_128B layout (8-row atoms, SBO = 1024 B between pixel groups,
+// LBO = distance between 32-channel chunks).  One tcgen05.mma (M=128, N=BLOCK_N, K=8 pixels) per 8-pixel atom.
+// A CTA owns one kernel row kh and all KW taps of it: the S tile is loaded once per stage and multiplied with the KW
+// shifted Bg tiles into KW separate TMEM accumulators (KW*BLOCK_N <= 384 columns).  The pixel range is split across
+// CTAs (split-K); partial results are added into the zero-initialised output with fp32 atomics.
+#include "tc_common.cuh"
+
+namespace gifb200 {
+namespace {
+
+constexpr int kWgStages = 3;
+constexpr int kPix = 32;                       // pixels (GEMM K) per stage
+constexpr int kChunkBytes = kPix * 128;        // one 32-channel x 32-pixel chunk = 4 KB
+constexpr int kAChunks = 4;                    // M = 128 small channels
+
+struct WgParams {
+    int B, Hs, Ws, Cs, Hb, Wb, Cb;
+    int k, pad, s2, flip;
+    int pw;                 // pixels per TMA row load (min(Ws, 32)); rows per stage = 32 / pw
+    long long units;        // number of 32-pixel units in the small grid
+    int splits;
+    long long stride_t, stride_cs, stride_cb;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;       // between 32-channel (MN) chunks
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;            // between 8-pixel (K) groups
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <int KW, int BLOCK_N>
+struct WgSmem {
+    static constexpr int kBChunks = BLOCK_N / 32;
+    static constexpr int kABytes = kAChunks * kChunkBytes;
+    static constexpr int kBBytesPerTap = kBChunks * kChunkBytes;
+    static constexpr int kStageBytes = kABytes + KW * kBBytesPerTap;
+    static constexpr int kBarrierOffset = kWgStages * kStageBytes;
+    static constexpr int kDynamic = kBarrierOffset + 128 + 1024;
+    static constexpr int kTmemCols = (KW * BLOCK_N <= 32) ? 32 : (KW * BLOCK_N <= 64) ? 64 : (KW * BLOCK_N <= 128) ? 128
+                                     : (KW * BLOCK_N <= 256) ? 256 : 512;
+};
+
+template <int KW, int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
+                                                          const __grid_constant__ CUtensorMap map_b,
+                                                          float* __restrict__ out, const WgParams p) {
+    using L = WgSmem<KW, BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+    uint64_t* empty_bar = full_bar + kWgStages;
+    uint64_t* tmem_full_bar = empty_bar + kWgStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int ms = blockIdx.x;                       // 128-channel tile of the small tensor
+    const int nb = blockIdx.y;                       // BLOCK_N-channel tile of the big tensor
+    const int kh = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const long long per = (p.units + p.splits - 1) / p.splits;
+    const long long u0 = split * per;
+    const long long u1 = u0 + per < p.units ? u0 + per : p.units;
+    const int iters = u1 > u0 ? static_cast<int>(u1 - u0) : 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_s) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(L::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (iters > 0) {
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
+            const int rows = kPix / p.pw;                    // rows of the small grid per stage
+            const int segs = p.Ws / p.pw;                    // 32-pixel segments per row (>= 1 when pw == 32)
+            const int row_bytes = p.pw * 128;
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                const long long u = u0 + it;
+                mbar_wait(&empty_bar[stage], ph ^ 1);
+                uint8_t* a_dst = smem + stage * L::kStageBytes;
+                uint8_t* b_dst = a_dst + L::kABytes;
+                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                for (int r = 0; r < rows; ++r) {
+                    long long grow;                          // global row index n*Hs + y
+                    int x0;
+                    if (rows == 1) { grow = u / segs; x0 = static_cast<int>(u % segs) * kPix; }
+                    else { grow = u * rows + r; x0 = 0; }
+                    const int n = static_cast<int>(grow / p.Hs), y = static_cast<int>(grow % p.Hs);
+                    for (int c = 0; c < kAChunks; ++c)
+                        tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                    for (int kw = 0; kw < KW; ++kw)
+                        for (int c = 0; c < L::kBChunks; ++c) {
+                            uint8_t* dst = b_dst + kw * L::kBBytesPerTap + c * kChunkBytes + r * row_bytes;
+                            const int ch = nb * BLOCK_N + c * 32;
+                            if (!p.s2)
+                                tma_load_4d(dst, &map_b, &full_bar[stage], ch, x0 + kw - p.pad, y + kh - p.pad, n);
+                            else
+                                tma_load_5d(dst, &map_b, &full_bar[stage], ch, kw & 1, x0 + (kw >> 1), 2 * y + kh, n);
+                        }
+                }
+                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer =====================
+            // MN-major operands: a_major = b_major = 1 (bits 15, 16)
+            constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N) | (1u << 15) | (1u << 16);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&full_bar[stage], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+                const uint64_t adesc = make_mnmajor_sw128_desc(a_addr, kChunkBytes);
+#pragma unroll
+                for (int kw = 0; kw < KW; ++kw) {
+                    const uint64_t bdesc = make_mnmajor_sw128_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
+#pragma unroll
+                    for (int j = 0; j < kPix / 8; ++j)   // 8 pixels per MMA: next swizzle atom = +1024 B (>>4 = 64)
+                        umma_tf32(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+            }
+            umma_commit(tmem_full_bar);
+        } else if (warp >= 4) {
+            // ===================== epilogue: TMEM -> fp32 atomics into the weight-gradient layout =====================
+            mbar_wait(tmem_full_bar, 0);
+            tcgen05_fence_after();
+            const int q = warp - 4;
+            const int cs = ms * 128 + q * 32 + lane;
+            const int T = p.k * p.k;
+#pragma unroll 1
+            for (int kw = 0; kw < KW; ++kw) {
+                const int t = kh * p.k + kw;
+                const int tt = p.flip ? T - 1 - t : t;
+                float* obase = out + tt * p.stride_t + cs * p.stride_cs + static_cast<long long>(nb) * BLOCK_N * p.stride_cb;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kw * BLOCK_N + c;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(obase + (c + j) * p.stride_cb, __uint_as_float(v[j]));
+                }
+            }
+            tcgen05_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::kTmemCols) : "memory");
+    }
+}
+
+inline bool pow2i(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+int pick_bn(int Cb) {
+    if (Cb % 128 == 0) return 128;
+    if (Cb % 64 == 0) return 64;
+    if (Cb % 32 == 0) return 32;
+    return 0;
+}
+
+template <int KW, int BLOCK_N>
+int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, const WgParams& p, cudaStream_t st) {
+    using L = WgSmem<KW, BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(wgrad_tc_kernel)", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid(p.Cs / 128, p.Cb / BLOCK_N, p.k * p.splits);
+    wgrad_tc_kernel<KW, BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ms, mb, out, p);
+    GIFB200_LAUNCH_CHECK("wgrad_tc_kernel");
+    return GIFB200_OK;
+}
+
+void roles(int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int mode, int& Hs, int& Ws, int& Cs, int& Hb, int& Wb, int& Cb) {
+    if (mode == 2) { Hs = Hi; Ws = Wi; Cs = Ci; Hb = Ho; Wb = Wo; Cb = Co; }
+    else { Hs = Ho; Ws = Wo; Cs = Co; Hb = Hi; Wb = Wi; Cb = Ci; }
+}
+
+}  // namespace
+
+bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode) {
+    if (B <= 0 || !(k == 3 || (k == 1 && mode == 0))) return false;
+    if (mode == 0 && !(Ho == Hi && Wo == Wi)) return false;
+    if (mode == 1 && !(Hi == 2 * Ho + 1 && Wi == 2 * Wo + 1)) return false;
+    if (mode == 2 && !(Ho == 2 * Hi + 1 && Wo == 2 * Wi + 1)) return false;
+    int Hs, Ws, Cs, Hb, Wb, Cb;
+    roles(Hi, Wi, Ci, Ho, Wo, Co, mode, Hs, Ws, Cs, Hb, Wb, Cb);
+    if (Cs % 128 != 0 || pick_bn(Cb) == 0) return false;
+    if (!pow2i(Hs) || !pow2i(Ws) || Ws < 4 || Hs < 4) return false;
+    if ((static_cast<long long>(B) * Hs * Ws) % kPix != 0) return false;
+    const int pw = Ws < kPix ? Ws : kPix;
+    if ((static_cast<long long>(B) * Hs) % (kPix / pw) != 0) return false;
+    return true;
+}
+
+int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
+                    int k, int mode, int flip, int transposed, cudaStream_t st) {
+    GIFB200_REQUIRE(conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE,
+                    "conv2d_wgrad_tc: unsupported shape");
+    GIFB200_REQUIRE(aligned16(x) && aligned16(gy), GIFB200_E_ALIGN, "conv2d_wgrad_tc: x / gy must be 16-byte aligned");
+    const int T = k * k;
+    cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * static_cast<size_t>(T) * Co * Ci, st);
+    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "wgrad memset", cudaGetErrorString(e));
+    WgParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.k = k; p.flip = flip;
+    roles(Hi, Wi, Ci, Ho, Wo, Co, mode, p.Hs, p.Ws, p.Cs, p.Hb, p.Wb, p.Cb);
+    const float* S = mode == 2 ? x : gy;
+    const float* Bg = mode == 2 ? gy : x;
+    p.s2 = mode != 0;
+    p.pad = mode == 0 ? k / 2 : 0;
+    p.pw = p.Ws < kPix ? p.Ws : kPix;
+    p.units = static_cast<long long>(B) * p.Hs * p.Ws / kPix;
+    // physical layout of gw: transposed ? [t][i][o] : [t][o][i];  small channels are o for S1/S2, i for T2
+    const long long stride_o = transposed ? 1 : Ci, stride_i = transposed ? Co : 1;
+    p.stride_cs = mode == 2 ? stride_i : stride_o;
+    p.stride_cb = mode == 2 ? stride_o : stride_i;
+    p.stride_t = static_cast<long long>(Co) * Ci;
+    const int bn = pick_bn(p.Cb);
+    const long long base_ctas = static_cast<long long>(p.Cs / 128) * (p.Cb / bn) * k;
+    long long splits = (kNumSMs + base_ctas - 1) / base_ctas;
+    if (splits > p.units) splits = p.units;
+    if (splits < 1) splits = 1;
+    p.splits = static_cast<int>(splits);
+    CUtensorMap ms, mb;
+    {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cs), static_cast<cuuint64_t>(p.Ws), static_cast<cuuint64_t>(p.Hs), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cs) * 4, static_cast<cuuint64_t>(p.Ws) * p.Cs * 4,
+                                       static_cast<cuuint64_t>(p.Hs) * p.Ws * p.Cs * 4};
+        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
+        int rc = encode_map(&ms, S, 4, dims, strides, box);
+        if (rc != GIFB200_OK) return rc;
+    }
+    if (!p.s2) {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cb), static_cast<cuuint64_t>(p.Wb), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Wb) * p.Cb * 4,
+                                       static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
+        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
+        int rc = encode_map(&mb, Bg, 4, dims, strides, box);
+        if (rc != GIFB200_OK) return rc;
+    } else {
+        const cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.Cb), 2, static_cast<cuuint64_t>((p.Wb + 1) / 2), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Cb) * 8,
+                                       static_cast<cuuint64_t>(p.Wb) * p.Cb * 4, static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
+        const cuuint32_t box[5] = {32, 1, static_cast<cuuint32_t>(p.pw), 1, 1};
+        int rc = encode_map(&mb, Bg, 5, dims, strides, box);
+        if (rc != GIFB200_OK) return rc;
+    }
+#define GIFB200_WG(KW, BN) launch_wg<KW, BN>(ms, mb, gw, p, st)
+    if (k == 3) return bn == 128 ? GIFB200_WG(3, 128) : bn == 64 ? GIFB200_WG(3, 64) : GIFB200_WG(3, 32);
+    return bn == 128 ? GIFB200_WG(1, 128) : bn == 64 ? GIFB200_WG(1, 64) : GIFB200_WG(1, 32);
+#undef GIFB200_WG
+}
+
+}  // namespace gifb200

@@ -19,6 +19,7 @@ from ._lib import check, lib, ptr, require_cuda, stream
 S1, S2, T2 = 0, 1, 2          # conv modes of gifb200_conv2d
 _ADJ_MODE = {S1: S1, S2: T2, T2: S2}
 CONV_IMPL = 0                 # 0 auto, 1 force SIMT fp32, 2 force tcgen05 (tests flip this)
+WGRAD_IMPL = 0                # same for the weight-gradient kernel
 _PRECISION = "tf32"
 
 
@@ -55,6 +56,8 @@ def _round_tf32_raw(x):
     y = torch.empty_like(x)
     check(lib.gifb200_axpby(ptr(x), None, ptr(y), x.numel(), 1.0, 0.0, 1, stream()), "gifb200_axpby(round)")
     return y
+
+PROFILE = None   # bench.py sets this to a list; every tensor-core conv launch then appends (ev0, ev1, flops, tag)
 
 _ws_cache = {}
 
@@ -96,8 +99,17 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw):
     if nws > 0 and not _is_tf32(x):          # tensor-core path: operands must be tf32-representable (see gifb200.h)
         x = _tag(_round_tf32_raw(x), True)
     ws = _workspace(nws, x.device)
+    prof = PROFILE is not None and nws > 0
+    if prof:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib.gifb200_conv2d(ptr(x), ptr(w), ptr(y), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip), int(transposed),
                              CONV_IMPL, ptr(ws), nws, stream()), "gifb200_conv2d")
+    if prof:
+        ev1.record()
+        pix = Hi * Wi if mode == T2 else Ho * Wo                    # algorithmic MACs: taps * Ci * Co per site
+        tag = "northstar" if (mode == S1 and Ci == 128 and Co == 128 and Ho == 256 and k == 3) else ""
+        PROFILE.append((ev0, ev1, 2.0 * B * pix * Ci * Co * k * k, tag))
     return y, x
 
 
@@ -107,7 +119,12 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
     _, Ho, Wo, Co = gy.shape
     shape = (k * k, Ci, Co) if transposed else (k * k, Co, Ci)
     gw = torch.empty(shape, dtype=torch.float32, device=x.device)
-    impl = 1 if CONV_IMPL == 1 else 0
+    impl = WGRAD_IMPL if CONV_IMPL != 1 else 1
+    if lib.gifb200_conv2d_wgrad_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl) > 0:   # tensor-core path
+        if not _is_tf32(x):
+            x = _round_tf32_raw(x)
+        if not _is_tf32(gy):
+            gy = _round_tf32_raw(gy)
     check(lib.gifb200_conv2d_wgrad(ptr(x), ptr(gy), ptr(gw), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip),
                                    int(transposed), impl, None, 0, stream()), "gifb200_conv2d_wgrad")
     return gw

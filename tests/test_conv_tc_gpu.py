@@ -1,0 +1,110 @@
+"""GPU: the tcgen05 (kind::tf32) implicit-GEMM convolution against the exact-fp32 SIMT kernel through the C ABI
+(impl=2 vs impl=1), every mode / flag combination, tile-edge shapes (4x4 images packed 8 per tile, batch not a multiple of
+the images-per-tile, ...).  Inputs are pre-rounded to tf32 so the only difference is the accumulation order: the bar is 2e-5
+for those, and 1e-3 (BASELINE.json) for raw fp32 inputs through gif_b200.ops (which rounds)."""
+import math
+
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def round_tf32(t):
+    from gif_b200 import ops
+    return ops._round_tf32_raw(t.contiguous())
+
+
+def run(x, w, k, mode, flip, transposed, impl):
+    from gif_b200 import ops
+    old = ops.CONV_IMPL
+    ops.CONV_IMPL = impl
+    try:
+        y, _ = ops._conv_raw(x, w, k, mode, flip, transposed,
+                             (ops.conv_out_size(x.shape[1], k, mode), ops.conv_out_size(x.shape[2], k, mode)))
+    finally:
+        ops.CONV_IMPL = old
+    return y
+
+
+CASES = [
+    # (B, Hs, Ws, Ci, Co, k, mode)   Hs/Ws = SITE grid (output for S1/S2, input for T2)
+    (2, 16, 16, 32, 32, 3, 0), (3, 4, 4, 64, 32, 3, 0), (5, 8, 8, 32, 64, 3, 0), (1, 32, 64, 64, 128, 3, 0),
+    (2, 128, 128, 32, 128, 3, 0), (2, 16, 16, 96, 256, 1, 0), (1, 256, 256, 32, 32, 3, 0),
+    (2, 16, 16, 32, 32, 3, 1), (3, 4, 4, 64, 64, 3, 1), (1, 64, 64, 32, 128, 3, 1), (2, 8, 32, 32, 32, 3, 1),
+    (2, 16, 16, 32, 32, 3, 2), (3, 4, 4, 64, 64, 3, 2), (1, 64, 64, 32, 128, 3, 2), (2, 8, 32, 32, 32, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", CASES)
+@pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
+def test_tc_matches_simt(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transposed):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Hs + Ci + mode)
+    Hi, Wi = (Hs, Ws) if mode != 1 else (2 * Hs + 1, 2 * Ws + 1)
+    x = round_tf32(torch.randn(B, Hi, Wi, Ci, device=cuda, generator=g))
+    wshape = (k * k, Ci, Co) if transposed else (k * k, Co, Ci)
+    w = round_tf32(torch.randn(*wshape, device=cuda, generator=g) / math.sqrt(Ci * k * k))
+    y_tc = run(x, w, k, mode, flip, transposed, 2)
+    y_ref = run(x, w, k, mode, flip, transposed, 1)
+    torch.cuda.synchronize()
+    assert y_tc.shape == y_ref.shape
+    e = gu.rel_err(y_tc.cpu().numpy(), y_ref.cpu().numpy())
+    assert e < 2e-5, e
+
+
+def test_tc_unrounded_inputs_within_1e3(cuda, tf32_mode):
+    """fp32 inputs through the public op: the wrapper rounds to tf32 (round-to-nearest); result within 1e-3 of exact fp32."""
+    from gif_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(2, 64, 64, 128, device=cuda, generator=g)
+    w = torch.randn(9, 128, 128, device=cuda, generator=g) / math.sqrt(1152)
+    y = ops.conv2d(x, w, 3, ops.S1)
+    ops.set_precision("fp32")
+    y32 = ops.conv2d(x, w, 3, ops.S1)
+    e = gu.rel_err(y.cpu().numpy(), y32.cpu().numpy())
+    assert 1e-6 < e < 1e-3, e     # > 1e-6: the tensor-core path really ran
+
+
+def test_tc_rejects_unsupported_shape(cuda):
+    from gif_b200 import ops
+    from gif_b200._lib import GifB200Error
+    with pytest.raises(GifB200Error):
+        run(torch.zeros(1, 9, 9, 32, device=cuda), torch.zeros(9, 32, 32, device=cuda), 3, 0, False, False, 2)
+
+
+WG_CASES = [
+    # (B, Hs, Ws, Ci, Co, k, mode)  site grid as above
+    (2, 16, 16, 32, 128, 3, 0), (4, 4, 4, 64, 128, 3, 0), (1, 32, 64, 128, 128, 3, 0), (2, 64, 64, 32, 256, 3, 0),
+    (2, 16, 16, 96, 128, 1, 0), (8, 8, 8, 32, 128, 3, 0),
+    (2, 16, 16, 32, 128, 3, 1), (4, 4, 4, 64, 128, 3, 1), (1, 64, 64, 64, 128, 3, 1),
+    (2, 16, 16, 128, 32, 3, 2), (4, 4, 4, 128, 64, 3, 2), (1, 64, 64, 128, 128, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", WG_CASES)
+@pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
+def test_wgrad_tc_matches_simt(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transposed):
+    from gif_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 77 + Hs + Ci + mode)
+    if mode == 0:
+        Hi, Wi, Ho, Wo = Hs, Ws, Hs, Ws
+    elif mode == 1:
+        Hi, Wi, Ho, Wo = 2 * Hs + 1, 2 * Ws + 1, Hs, Ws
+    else:
+        Hi, Wi, Ho, Wo = Hs, Ws, 2 * Hs + 1, 2 * Ws + 1
+    x = round_tf32(torch.randn(B, Hi, Wi, Ci, device=cuda, generator=g))
+    gy = round_tf32(torch.randn(B, Ho, Wo, Co, device=cuda, generator=g))
+    res = []
+    for impl in (2, 1):
+        old = (ops.CONV_IMPL, ops.WGRAD_IMPL)
+        ops.CONV_IMPL, ops.WGRAD_IMPL = (0, 2) if impl == 2 else (1, 1)
+        try:
+            res.append(ops._wgrad_raw(x, gy, k, mode, flip, transposed))
+        finally:
+            ops.CONV_IMPL, ops.WGRAD_IMPL = old
+    torch.cuda.synchronize()
+    assert res[0].shape == res[1].shape
+    e = gu.rel_err(res[0].cpu().numpy(), res[1].cpu().numpy())
+    assert e < 5e-5, e

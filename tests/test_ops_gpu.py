@@ -56,7 +56,7 @@ def test_upfirdn2d_golden(cuda):
 
 @pytest.mark.parametrize("c", [4, 32, 5])
 @pytest.mark.parametrize("up,down,pad", [(1, 1, (2, 2)), (2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (1, 1))])
-def test_upfirdn2d_backward_and_double_backward(cuda, c, up, down, pad):
+def test_upfirdn2d_backward_and_double_backward(cuda, fp32_mode, c, up, down, pad):
     """vectorised (C%4==0) and scalar paths; first and second derivative against the oracle's autograd."""
     from gif_b200 import ops
     k = gu.randn((4, 4), 5)      # asymmetric: the adjoint must flip
