@@ -95,11 +95,27 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def usable_cores():
+    """Host cores this process may really use: affinity mask, capped by the cgroup CPU quota (a 128-thread pool on a
+    quota-limited container runs ~30x slower than a right-sized one) and by 32 (torch's conv kernels stop scaling)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))
+
+
 def cpu_arm(steps, warmup):
     """The oracle port on the host cores: one D+G iteration at batch 1, 256^2 (no R1 / PPL) per step."""
     import golden_util as gu
     from oracle import stylegan2_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     sdg = gu.seeded_state_dict(gu.g_shapes(100), 1)
     sdd = gu.seeded_state_dict(gu.d_shapes(RES), 3)
@@ -240,6 +256,15 @@ def main():
     roof = None
     if prof:
         torch.cuda.synchronize()
+        shapes = {}
+        for a, b, f, tag, key in prof:
+            e = shapes.setdefault(key, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += a.elapsed_time(b); e[2] += f
+        if os.environ.get("GIFB200_SHAPE_PROFILE"):
+            with open(os.environ["GIFB200_SHAPE_PROFILE"], "w") as fh:
+                for key, (n, t, f) in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                    fh.write(f"{key}  launches={n}  ms={t:.3f}  TFLOP/s={f / (t * 1e-3) / 1e12 if t > 0 else 0:.1f}\n")
+        prof = [(a, b, f, tag) for a, b, f, tag, key in prof if key[0] == "conv"]
         tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
         tot_fl = sum(f for _, _, f, _ in prof)
         peaks = {}

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
         const int tt = p.flip ? T - 1 - t : t;
         int yi = 0, xi = 0;
         const bool src_ok = a_ok && tap_source<MODE>(p, a_yo, a_xo, kh, kw, yi, xi);
+        if (MODE == 2 && !__syncthreads_or(src_ok)) continue;   // no pixel of this tile reads this tap (T2 parity / border)
         const float* xrow = x + ((static_cast<long long>(a_b) * p.Hi + yi) * p.Wi + xi) * p.Ci;
         const float* wt = w + static_cast<long long>(tt) * p.Co * p.Ci;
         for (int c0 = 0; c0 < p.Ci; c0 += BK) {

@@ -4,12 +4,19 @@
 //   Bg = "big" tensor (B,Hb,Wb,Cb) read at map(p,t) = (y+kh-pad, x+kw-pad)  (S1)  or (2y+kh, 2x+kw)  (S2 / T2)
 //
 // GEMM view per CTA: M = 128 small channels, N = BLOCK_N big channels, K = pixels.  Both operands are
-// channels-last, i.e. MN-contiguous ("MN-major"): a TMA box (32 channels x P pixels) lands as P rows of 128 bytes,
-// which is exactly the canonical MN-major SWIZZLE_128B layout (8-row atoms, SBO = 1024 B between pixel groups,
-// LBO = distance between 32-channel chunks).  One tcgen05.mma (M=128, N=BLOCK_N, K=8 pixels) per 8-pixel atom.
+// channels-last, i.e. MN-contiguous ("MN-major"): a TMA box (32 channels x P pixels) lands as P rows of 128 bytes.
+// For 32-bit MN-major operands the only legal UMMA shared-memory layout is SWIZZLE_128B_BASE32B (32-byte chunks
+// XOR-ed with the row index mod 4; cutlass sm100_common.inl:92) -- the TMA side is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// Descriptor: 4-row K atoms (SBO = 512 B between them), LBO = distance between 32-channel chunks.  One tcgen05.mma
+// (M=128, N=BLOCK_N, K=8 pixels) consumes two K atoms; the next 8 pixels are +1024 B.
 // A CTA owns one kernel row kh and all KW taps of it: the S tile is loaded once per stage and multiplied with the KW
 // shifted Bg tiles into KW separate TMEM accumulators (KW*BLOCK_N <= 384 columns).  The pixel range is split across
 // CTAs (split-K); partial results are added into the zero-initialised output with fp32 atomics.
+//
+// STACK variant (Cs == 32, stride-1 3x3: the zero-padded NoiseInjection convs): M = 128 cannot be filled with channels,
+// so the four 32-row chunks of the A tile hold the SAME 32 channels of S at three different row shifts (dy = +1, 0, -1;
+// the 4th chunk is a duplicate) -- chunk kh then accumulates kernel row kh, the KW shifted Bg tiles give the kernel
+// columns, and ONE CTA produces all 9 taps (no kh split).
 #include "tc_common.cuh"
 
 namespace gifb200 {
@@ -29,13 +36,13 @@ struct WgParams {
     long long stride_t, stride_cs, stride_cb;
 };
 
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;       // between 32-channel (MN) chunks
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;            // between 8-pixel (K) groups
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;             // between 4-pixel (K) swizzle atoms
+    d |= static_cast<uint64_t>(1) << 46;                    // descriptor version (sm_100)
+    d |= static_cast<uint64_t>(1) << 61;                    // LayoutType::SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -51,7 +58,7 @@ struct WgSmem {
                                      : (KW * BLOCK_N <= 256) ? 256 : 512;
 };
 
-template <int KW, int BLOCK_N>
+template <int KW, int BLOCK_N, bool STACK>
 __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
                                                           const __grid_constant__ CUtensorMap map_b,
                                                           float* __restrict__ out, const WgParams p) {
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
 
     const int ms = blockIdx.x;                       // 128-channel tile of the small tensor
     const int nb = blockIdx.y;                       // BLOCK_N-channel tile of the big tensor
-    const int kh = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const int kh = STACK ? 0 : blockIdx.z / p.splits, split = STACK ? blockIdx.z : blockIdx.z % p.splits;
     const long long per = (p.units + p.splits - 1) / p.splits;
     const long long u0 = split * per;
     const long long u1 = u0 + per < p.units ? u0 + per : p.units;
@@ -111,13 +118,20 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                     if (rows == 1) { grow = u / segs; x0 = static_cast<int>(u % segs) * kPix; }
                     else { grow = u * rows + r; x0 = 0; }
                     const int n = static_cast<int>(grow / p.Hs), y = static_cast<int>(grow % p.Hs);
-                    for (int c = 0; c < kAChunks; ++c)
-                        tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                    for (int c = 0; c < kAChunks; ++c) {
+                        if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
+                            tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], 0, x0,
+                                        y + 1 - (c < 3 ? c : 2), n);
+                        else
+                            tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                    }
                     for (int kw = 0; kw < KW; ++kw)
                         for (int c = 0; c < L::kBChunks; ++c) {
                             uint8_t* dst = b_dst + kw * L::kBBytesPerTap + c * kChunkBytes + r * row_bytes;
                             const int ch = nb * BLOCK_N + c * 32;
-                            if (!p.s2)
+                            if (STACK)
+                                tma_load_4d(dst, &map_b, &full_bar[stage], ch, x0 + kw - 1, y, n);
+                            else if (!p.s2)
                                 tma_load_4d(dst, &map_b, &full_bar[stage], ch, x0 + kw - p.pad, y + kh - p.pad, n);
                             else
                                 tma_load_5d(dst, &map_b, &full_bar[stage], ch, kw & 1, x0 + (kw >> 1), 2 * y + kh, n);
@@ -135,10 +149,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                 mbar_wait(&full_bar[stage], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-                const uint64_t adesc = make_mnmajor_sw128_desc(a_addr, kChunkBytes);
+                const uint64_t adesc = make_mnmajor_sw128b32_desc(a_addr, kChunkBytes);
 #pragma unroll
                 for (int kw = 0; kw < KW; ++kw) {
-                    const uint64_t bdesc = make_mnmajor_sw128_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
+                    const uint64_t bdesc = make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
 #pragma unroll
                     for (int j = 0; j < kPix / 8; ++j)   // 8 pixels per MMA: next swizzle atom = +1024 B (>>4 = 64)
                         umma_tf32(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
@@ -152,11 +166,12 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
             mbar_wait(tmem_full_bar, 0);
             tcgen05_fence_after();
             const int q = warp - 4;
-            const int cs = ms * 128 + q * 32 + lane;
+            const int cs = STACK ? lane : ms * 128 + q * 32 + lane;
             const int T = p.k * p.k;
 #pragma unroll 1
             for (int kw = 0; kw < KW; ++kw) {
-                const int t = kh * p.k + kw;
+                if (STACK && q == 3) break;                     // duplicate chunk
+                const int t = (STACK ? q : kh) * p.k + kw;
                 const int tt = p.flip ? T - 1 - t : t;
                 float* obase = out + tt * p.stride_t + cs * p.stride_cs + static_cast<long long>(nb) * BLOCK_N * p.stride_cb;
 #pragma unroll 1
@@ -196,17 +211,17 @@ int pick_bn(int Cb) {
     return 0;
 }
 
-template <int KW, int BLOCK_N>
+template <int KW, int BLOCK_N, bool STACK>
 int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, const WgParams& p, cudaStream_t st) {
     using L = WgSmem<KW, BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(wgrad_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid(p.Cs / 128, p.Cb / BLOCK_N, p.k * p.splits);
-    wgrad_tc_kernel<KW, BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ms, mb, out, p);
+    dim3 grid(STACK ? 1 : p.Cs / 128, p.Cb / BLOCK_N, STACK ? p.splits : p.k * p.splits);
+    wgrad_tc_kernel<KW, BLOCK_N, STACK><<<grid, 256, L::kDynamic, st>>>(ms, mb, out, p);
     GIFB200_LAUNCH_CHECK("wgrad_tc_kernel");
     return GIFB200_OK;
 }
@@ -225,7 +240,8 @@ bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, in
     if (mode == 2 && !(Ho == 2 * Hi + 1 && Wo == 2 * Wi + 1)) return false;
     int Hs, Ws, Cs, Hb, Wb, Cb;
     roles(Hi, Wi, Ci, Ho, Wo, Co, mode, Hs, Ws, Cs, Hb, Wb, Cb);
-    if (Cs % 128 != 0 || pick_bn(Cb) == 0) return false;
+    const bool stack = (Cs == 32 && mode == 0 && k == 3);
+    if ((Cs % 128 != 0 && !stack) || pick_bn(Cb) == 0) return false;
     if (!pow2i(Hs) || !pow2i(Ws) || Ws < 4 || Hs < 4) return false;
     if ((static_cast<long long>(B) * Hs * Ws) % kPix != 0) return false;
     const int pw = Ws < kPix ? Ws : kPix;
@@ -257,7 +273,8 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
     p.stride_cb = mode == 2 ? stride_o : stride_i;
     p.stride_t = static_cast<long long>(Co) * Ci;
     const int bn = pick_bn(p.Cb);
-    const long long base_ctas = static_cast<long long>(p.Cs / 128) * (p.Cb / bn) * k;
+    const bool stack = (p.Cs == 32 && mode == 0 && k == 3);
+    const long long base_ctas = stack ? (p.Cb / bn) : static_cast<long long>(p.Cs / 128) * (p.Cb / bn) * k;
     long long splits = (kNumSMs + base_ctas - 1) / base_ctas;
     if (splits > p.units) splits = p.units;
     if (splits < 1) splits = 1;
@@ -268,7 +285,7 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cs) * 4, static_cast<cuuint64_t>(p.Ws) * p.Cs * 4,
                                        static_cast<cuuint64_t>(p.Hs) * p.Ws * p.Cs * 4};
         const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&ms, S, 4, dims, strides, box);
+        int rc = encode_map(&ms, S, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     }
     if (!p.s2) {
@@ -276,17 +293,20 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Wb) * p.Cb * 4,
                                        static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
         const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&mb, Bg, 4, dims, strides, box);
+        int rc = encode_map(&mb, Bg, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     } else {
         const cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.Cb), 2, static_cast<cuuint64_t>((p.Wb + 1) / 2), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[4] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Cb) * 8,
                                        static_cast<cuuint64_t>(p.Wb) * p.Cb * 4, static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
         const cuuint32_t box[5] = {32, 1, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&mb, Bg, 5, dims, strides, box);
+        int rc = encode_map(&mb, Bg, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     }
-#define GIFB200_WG(KW, BN) launch_wg<KW, BN>(ms, mb, gw, p, st)
+#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false>(ms, mb, gw, p, st)
+    if (stack)
+        return bn == 128 ? launch_wg<3, 128, true>(ms, mb, gw, p, st)
+               : bn == 64 ? launch_wg<3, 64, true>(ms, mb, gw, p, st) : launch_wg<3, 32, true>(ms, mb, gw, p, st);
     if (k == 3) return bn == 128 ? GIFB200_WG(3, 128) : bn == 64 ? GIFB200_WG(3, 64) : GIFB200_WG(3, 32);
     return bn == 128 ? GIFB200_WG(1, 128) : bn == 64 ? GIFB200_WG(1, 64) : GIFB200_WG(1, 32);
 #undef GIFB200_WG

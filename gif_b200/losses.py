@@ -51,8 +51,11 @@ class PathLengthRegularizor:
         pl_noise = pl_noise / np.sqrt(np.prod(fake.shape))                       # losses.py:114
         pl_grads = grad(outputs=torch.sum(fake * pl_noise), inputs=w, create_graph=True)[0]
         pl_lengths = torch.mean(torch.sqrt(torch.sum(torch.pow(pl_grads, 2), dim=1)))   # losses.py:116
-        self.pl_moving_mean = self.pl_moving_mean + self.pl_decay * pl_lengths.detach() - self.pl_moving_mean  # :119
-        return torch.pow(pl_lengths - self.pl_moving_mean, 2)                    # losses.py:122
+        # losses.py:119 as written (no stop-gradient: the new mean == decay * length and carries its gradient into the
+        # penalty); only the value kept for the next call is detached so that no graph outlives the iteration.
+        ema = self.pl_moving_mean + self.pl_decay * pl_lengths - self.pl_moving_mean
+        self.pl_moving_mean = ema.detach()
+        return torch.pow(pl_lengths - ema, 2)                                    # losses.py:122
 
 
 def _synth_from_w(g, w, cond, step):

@@ -109,7 +109,7 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw):
         ev1.record()
         pix = Hi * Wi if mode == T2 else Ho * Wo                    # algorithmic MACs: taps * Ci * Co per site
         tag = "northstar" if (mode == S1 and Ci == 128 and Co == 128 and Ho == 256 and k == 3) else ""
-        PROFILE.append((ev0, ev1, 2.0 * B * pix * Ci * Co * k * k, tag))
+        PROFILE.append((ev0, ev1, 2.0 * B * pix * Ci * Co * k * k, tag, ("conv", mode, B, Hi, Wi, Ci, Co, k)))
     return y, x
 
 
@@ -125,8 +125,16 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
             x = _round_tf32_raw(x)
         if not _is_tf32(gy):
             gy = _round_tf32_raw(gy)
+    prof = PROFILE is not None
+    if prof:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib.gifb200_conv2d_wgrad(ptr(x), ptr(gy), ptr(gw), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip),
                                    int(transposed), impl, None, 0, stream()), "gifb200_conv2d_wgrad")
+    if prof:
+        ev1.record()
+        pix = Hi * Wi if mode == T2 else Ho * Wo
+        PROFILE.append((ev0, ev1, 2.0 * B * pix * Ci * Co * k * k, "wgrad", ("wgrad", mode, B, Hi, Wi, Ci, Co, k)))
     return gw
 
 

@@ -252,6 +252,8 @@ def path_length_penalty(cond, input_indices, sd, pl_noise, pl_mean=0.0, step=6, 
     create_graph=True so the penalty has a gradient.  Returns (penalty, new_ema, length)."""
     z = sd["image_embedding.embd_weight"][input_indices]
     w = mapping_network(z, sd)
+    if not w.requires_grad:            # mapping weights frozen in the caller's state dict: w is then the leaf
+        w = w.detach().requires_grad_(True)
     img = synthesis(w, cond, sd, step)
     y = pl_noise / math.sqrt(img.numel())
     (g,) = torch.autograd.grad((img * y).sum(), w, create_graph=True)

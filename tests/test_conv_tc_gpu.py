@@ -80,6 +80,8 @@ WG_CASES = [
     (2, 16, 16, 96, 128, 1, 0), (8, 8, 8, 32, 128, 3, 0),
     (2, 16, 16, 32, 128, 3, 1), (4, 4, 4, 64, 128, 3, 1), (1, 64, 64, 64, 128, 3, 1),
     (2, 16, 16, 128, 32, 3, 2), (4, 4, 4, 128, 64, 3, 2), (1, 64, 64, 128, 128, 3, 2),
+    # STACK variant (Cs == 32): the zero-padded NoiseInjection convs
+    (2, 16, 16, 32, 32, 3, 0), (4, 4, 4, 32, 32, 3, 0), (1, 64, 128, 64, 32, 3, 0), (3, 8, 8, 128, 32, 3, 0),
 ]
 
 
