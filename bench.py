@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -199,7 +200,10 @@ def main():
         for s in range(n):
             if e2e:
                 hb = host[s % n_host]
-                real, cond, idx = (t.to(dev, non_blocking=True) for t in hb)
+                if trainer._graphs is not None:
+                    real, cond, idx = hb           # copied from pinned host memory straight into the graphs' input buffers
+                else:
+                    real, cond, idx = (t.to(dev, non_blocking=True) for t in hb)
             else:
                 real, cond, idx = resident[s % n_host]
             out = trainer.train_iteration(real, cond, idx)
@@ -229,17 +233,42 @@ def main():
     trainer.iteration = 16 - args.warmup
     run(args.warmup, False)
     barrier()
+    graph_note = "off (--no-graph)"
+    if not args.no_graph:
+        try:
+            trainer.capture(B, RES)
+            trainer.iteration = 14
+            run(2, False)                      # one replay of each graph before timing
+            barrier()
+            graph_note = "2 CUDA graphs per rank (iteration with / without R1), replayed"
+        except Exception as e:                 # capture is an optimisation of the launch path, never a different compute path
+            trainer._graphs = None
+            graph_note = f"capture failed, eager launches: {type(e).__name__}: {str(e)[:200]}"
+            torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ops.PROFILE = [] if rank == 0 else None
+    trainer.replayed_launches = 0
+    use_graph = trainer._graphs is not None
+    ops.PROFILE = [] if (rank == 0 and not use_graph) else None
     ms = timed(args.steps, False)
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() - launches0 + trainer.replayed_launches
     prof = ops.PROFILE
     ops.PROFILE = None
     clocks = sampler.stop() if rank == 0 else None
+    prof_note = "per-launch CUDA events inside the timed region"
+    if use_graph and rank == 0:
+        # graph replays cannot carry per-launch events: time the same kernels in a separate eager pass of the same steps
+        saved, trainer._graphs = trainer._graphs, None
+        ops.PROFILE = []
+        timed(min(args.steps, 4), False)
+        prof = ops.PROFILE
+        ops.PROFILE = None
+        trainer._graphs = saved
+        prof_note = ("per-launch CUDA events in a separate eager pass of %d steps after the timed region (CUDA-graph replays "
+                     "cannot carry events; same kernels, same shapes)" % min(args.steps, 4))
     value = world * B * args.steps / (ms / 1000.0)
 
     e2e = None
@@ -267,6 +296,7 @@ def main():
         prof = [(a, b, f, tag) for a, b, f, tag, key in prof if key[0] == "conv"]
         tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
         tot_fl = sum(f for _, _, f, _ in prof)
+        prof_steps = min(args.steps, 4) if use_graph else args.steps
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -280,8 +310,8 @@ def main():
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate; no tf32 entry"
                                 " in the file)") if bf16 else "fallback 1.4 PFLOP/s sustained bf16 / 2",
-                "launches": len(prof), "kernel_ms_per_step": tot_ms / args.steps,
-                "share_of_step": tot_ms / ms,
+                "launches": len(prof), "kernel_ms_per_step": tot_ms / prof_steps,
+                "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note,
                 "northstar_layer_tflops": (sum(f for _, f in ns) / (sum(t for t, _ in ns) * 1e-3) / 1e12) if ns else None}
     cb = None
     if not args.no_cpu_baseline:
@@ -291,7 +321,7 @@ def main():
             "vs_baseline": None, "dtype": "tf32 tensor-core contraction, f32 accumulate/storage", "data": "synthetic",
             "config": {"workload": "train_step_256_bs32: StyledGenerator(70000 ids) + Discriminator(256, 9ch), D step + G step, "
                                    "Adam, EMA, R1 every 16th iteration" + ("" if args.no_ppl else ", path-length reg every iteration"),
-                       "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}",
+                       "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}", "cuda_graph": graph_note,
                        "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb}
     print(json.dumps(line))

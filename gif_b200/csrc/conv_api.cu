@@ -13,8 +13,9 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
               int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st);
 // conv_wgrad_tc.cu
 bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
+size_t conv2d_wgrad_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
 int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                    int k, int mode, int flip, int transposed, cudaStream_t st);
+                    int k, int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace gifb200
 
 using namespace gifb200;
@@ -38,22 +39,22 @@ extern "C" int gifb200_conv2d(const float* x, const float* w, float* y, int B, i
     return conv2d_simt(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, st);
 }
 
-// no scratch memory is needed (kept in the ABI for future use); the return value doubles as "tensor-core path" flag
+// > 0 exactly when the tcgen05 path will be taken (split-K partial sums live in the workspace)
 extern "C" size_t gifb200_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
                                                        int mode, int impl) {
     if (impl == 1) return 0;
-    return conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode) ? 16 : 0;
+    return conv2d_wgrad_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
 }
 
 extern "C" int gifb200_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho,
-                                    int Wo, int Co, int k, int mode, int flip, int transposed, int impl, void*, size_t,
-                                    gifb200_stream_t stream) {
+                                    int Wo, int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,
+                                    size_t workspace_bytes, gifb200_stream_t stream) {
     GIFB200_REQUIRE(impl >= 0 && impl <= 2, GIFB200_E_SHAPE, "conv2d_wgrad: impl must be 0, 1 or 2");
     const bool tc_ok = conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (impl == 2 && !tc_ok) return fail(GIFB200_E_SHAPE, "conv2d_wgrad: shape not supported by the tcgen05 path");
     if (impl != 1 && tc_ok)
-        return conv2d_wgrad_tc(x, gy, gw, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed,
-                               static_cast<cudaStream_t>(stream));
+        return conv2d_wgrad_tc(x, gy, gw, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream));
     return conv2d_wgrad_simt(x, gy, gw, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed,
                              static_cast<cudaStream_t>(stream));
 }

@@ -56,34 +56,35 @@ struct SmemLayout {
     static constexpr int kBTileBytes = BLOCK_N * kBlockK * 4;
     static constexpr int kStageBytes = kATileBytes + kBTileBytes;
     static constexpr int kBarrierOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarrierOffset + 128;   // full[3], empty[3], tmem_full, tmem ptr
+    static constexpr int kTotal = kBarrierOffset + 128;   // full[3], empty[3], tmem_full[2], tmem_empty[2], tmem ptr
     static constexpr int kDynamic = kTotal + 1024;        // slack for manual 1024 B alignment
+    static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator buffers
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (<= 2 per SM) walk the tile list  tile = ((phase * nblocks + nblk) * mtiles + mtile).
+// The smem ring and its phase bits run continuously across tiles; the TMEM accumulator is double buffered so the
+// epilogue of tile i overlaps the main loop of tile i+1 of the same CTA (and the second resident CTA fills the rest).
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
-                                                         float* __restrict__ y, const TcParams p) {
+                                                         float* __restrict__ y, const TcParams p, const int mtiles,
+                                                         const int total_tiles) {
     using L = SmemLayout<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
     uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + kStages;        // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- tile coordinates
-    const int phase = blockIdx.z;
-    int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-    const int n0 = tile * p.nt, y0 = ty * p.ht, x0 = tx * p.wt;
-    const int nblk = blockIdx.y;
-    const int ntaps = p.phase_ntaps[phase];
+    const int nblocks = p.Co / BLOCK_N;
     const int kchunks = p.Ci / kBlockK;
-    const int iters = ntaps * kchunks;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(BLOCK_N) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(L::kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -108,83 +109,115 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t ph = 0;
-        for (int it = 0; it < iters; ++it) {
-            const int tap = it / kchunks, c0 = (it % kchunks) * kBlockK;
-            mbar_wait(&empty_bar[stage], ph ^ 1);
-            uint8_t* a_dst = smem + stage * L::kStageBytes;
-            uint8_t* b_dst = a_dst + kATileBytes;
-            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-            const int dy = p.tap_dy[phase][tap], dx = p.tap_dx[phase][tap];
-            if (!p.s2) {
-                tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
-            } else {
-                const int par = p.tap_par[phase][tap];
-                const int row_bytes = p.wt * kBlockK * 4;
-                for (int n = 0; n < p.nt; ++n)
-                    for (int h = 0; h < p.ht; ++h)
-                        tma_load_5d(a_dst + (n * p.ht + h) * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
-                                    (y0 + h) * p.in_sy + dy, n0 + n);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int mt = t % mtiles; t /= mtiles;
+            const int nblk = t % nblocks;
+            const int phase = t / nblocks;
+            int m = mt;
+            const int tx = m % p.tiles_x; m /= p.tiles_x;
+            const int ty = m % p.tiles_y; m /= p.tiles_y;
+            const int n0 = m * p.nt, y0 = ty * p.ht, x0 = tx * p.wt;
+            const int iters = p.phase_ntaps[phase] * kchunks;
+            for (int it = 0; it < iters; ++it) {
+                const int tap = it / kchunks, c0 = (it % kchunks) * kBlockK;
+                mbar_wait(&empty_bar[stage], ph ^ 1);
+                uint8_t* a_dst = smem + stage * L::kStageBytes;
+                uint8_t* b_dst = a_dst + kATileBytes;
+                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                const int dy = p.tap_dy[phase][tap], dx = p.tap_dx[phase][tap];
+                if (!p.s2) {
+                    tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+                } else {
+                    const int par = p.tap_par[phase][tap];
+                    const int row_bytes = p.wt * kBlockK * 4;
+                    for (int n = 0; n < p.nt; ++n)
+                        for (int h = 0; h < p.ht; ++h)
+                            tma_load_5d(a_dst + (n * p.ht + h) * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
+                                        (y0 + h) * p.in_sy + dy, n0 + n);
+                }
+                tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+                if (++stage == kStages) { stage = 0; ph ^= 1; }
             }
-            tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
-            if (++stage == kStages) { stage = 0; ph ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = make_idesc_tf32(kBlockM, BLOCK_N);
         int stage = 0;
         uint32_t ph = 0;
-        for (int it = 0; it < iters; ++it) {
-            mbar_wait(&full_bar[stage], ph);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            const int phase = tile / (mtiles * nblocks);
+            const int iters = p.phase_ntaps[phase] * kchunks;
+            const int buf = local & 1;
+            mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);     // epilogue has drained this buffer
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-            const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-            const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
+            const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&full_bar[stage], ph);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
-                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-            umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
-            if (++stage == kStages) { stage = 0; ph ^= 1; }
+                for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
+                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+                if (++stage == kStages) { stage = 0; ph ^= 1; }
+            }
+            umma_commit(&tmem_full_bar[buf]);            // accumulator complete
         }
-        umma_commit(tmem_full_bar);                  // accumulator complete
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
         const int q = warp - 4;                      // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                 // tile row == TMEM lane
         const int w_in = r % p.wt, h_in = (r / p.wt) % p.ht, n_in = r / (p.wt * p.ht);
-        const int n = n0 + n_in;
-        const int Y = (y0 + h_in) * p.oys + p.phase_oy0[phase], X = (x0 + w_in) * p.oxs + p.phase_ox0[phase];
-        const bool ok = n < p.B && Y < p.Ho && X < p.Wo;
-        float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            int t = tile;
+            const int mt = t % mtiles; t /= mtiles;
+            const int nblk = t % nblocks;
+            const int phase = t / nblocks;
+            int m = mt;
+            const int tx = m % p.tiles_x; m /= p.tiles_x;
+            const int ty = m % p.tiles_y; m /= p.tiles_y;
+            const int n = m * p.nt + n_in;
+            const int Y = (ty * p.ht + h_in) * p.oys + p.phase_oy0[phase], X = (tx * p.wt + w_in) * p.oxs + p.phase_ox0[phase];
+            const bool ok = n < p.B && Y < p.Ho && X < p.Wo;
+            float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N;
+            const int buf = local & 1;
+            mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+            tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ok) {
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + c;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + c + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + c + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
+                }
             }
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty_bar[buf]);       // 128 arrivals release the buffer to the MMA issuer
         }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BLOCK_N) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::kTmemCols) : "memory");
     }
 }
 
@@ -227,8 +260,10 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* y, const TcParam
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(conv_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid(mtiles, p.Co / BLOCK_N, p.nphase);
-    conv_tc_kernel<BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ma, mb, y, p);
+    const long long total = static_cast<long long>(mtiles) * (p.Co / BLOCK_N) * p.nphase;
+    if (total > 2147483647LL) return fail(GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
+    const int grid = total < 2 * kNumSMs ? static_cast<int>(total) : 2 * kNumSMs;   // persistent: <= 2 CTAs per SM
+    conv_tc_kernel<BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ma, mb, y, p, mtiles, static_cast<int>(total));
     GIFB200_LAUNCH_CHECK("conv_tc_kernel");
     return GIFB200_OK;
 }
@@ -259,6 +294,23 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     GIFB200_REQUIRE(aligned16(x) && aligned16(y), GIFB200_E_ALIGN, "conv2d_tc: x / y must be 16-byte aligned");
     const int T = k * k;
     float* wst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+    // T2: the last output row / column (about 1/128 of the pixels, exact fp32 SIMT) runs concurrently on an auxiliary stream
+    // (event fork/join: stream-ordered, capturable in CUDA graphs, no host synchronisation).
+    static cudaStream_t aux = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (mode == 2) {
+        if (!aux) {
+            if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
+                return fail(GIFB200_E_CUDA, "conv2d_tc: cannot create the auxiliary stream");
+        }
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
+        int rcs = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, aux);
+        cudaEventRecord(ev_join, aux);
+        if (rcs != GIFB200_OK) { cudaStreamWaitEvent(st, ev_join, 0); return rcs; }
+    }
     {
         const long long total = static_cast<long long>(T) * Co * Ci;
         int blocks = cdiv(total, 256 * 4);
@@ -335,10 +387,11 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     if (bn == 128) rc = launch<128>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else if (bn == 64) rc = launch<64>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else rc = launch<32>(ma, mb, y, p, static_cast<int>(mtiles), st);
-    if (rc != GIFB200_OK) return rc;
-    if (mode == 2)   // last output row / column of the transposed convolution (exact fp32 SIMT, ~1/128 of the pixels)
-        return conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, st);
-    return GIFB200_OK;
+    if (mode == 2) {
+        cudaError_t e = cudaStreamWaitEvent(st, ev_join, 0);      // join: later work on `st` sees the strip
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "conv2d_tc: join", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 }  // namespace gifb200

@@ -34,6 +34,7 @@ struct WgParams {
     long long units;        // number of 32-pixel units in the small grid
     int splits;
     long long stride_t, stride_cs, stride_cb;
+    long long part_stride;   // floats per split in the partial buffer: T * Cs_total * Cb (layout [split][t][cs][cb])
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -61,7 +62,7 @@ struct WgSmem {
 template <int KW, int BLOCK_N, bool STACK>
 __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
                                                           const __grid_constant__ CUtensorMap map_b,
-                                                          float* __restrict__ out, const WgParams p) {
+                                                          float* __restrict__ part, const WgParams p) {
     using L = WgSmem<KW, BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -99,8 +100,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (iters > 0) {
-        if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
+        if ((warp == 0 || warp == 3) && lane == 0) {
+            // ===================== TMA producers =====================
+            // Two issuing threads share the work of a stage (16 box loads of 4 KB): warp 0 arms the barrier and loads the
+            // S tile + the first Bg tap, warp 3 loads the remaining taps.  Both wait on the same empty barrier.
+            const bool first = warp == 0;
             const int rows = kPix / p.pw;                    // rows of the small grid per stage
             const int segs = p.Ws / p.pw;                    // 32-pixel segments per row (>= 1 when pw == 32)
             const int row_bytes = p.pw * 128;
@@ -111,21 +115,23 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                 mbar_wait(&empty_bar[stage], ph ^ 1);
                 uint8_t* a_dst = smem + stage * L::kStageBytes;
                 uint8_t* b_dst = a_dst + L::kABytes;
-                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                if (first) mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                 for (int r = 0; r < rows; ++r) {
                     long long grow;                          // global row index n*Hs + y
                     int x0;
                     if (rows == 1) { grow = u / segs; x0 = static_cast<int>(u % segs) * kPix; }
                     else { grow = u * rows + r; x0 = 0; }
                     const int n = static_cast<int>(grow / p.Hs), y = static_cast<int>(grow % p.Hs);
-                    for (int c = 0; c < kAChunks; ++c) {
-                        if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
-                            tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], 0, x0,
-                                        y + 1 - (c < 3 ? c : 2), n);
-                        else
-                            tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                    if (first) {
+                        for (int c = 0; c < kAChunks; ++c) {
+                            if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
+                                tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], 0, x0,
+                                            y + 1 - (c < 3 ? c : 2), n);
+                            else
+                                tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                        }
                     }
-                    for (int kw = 0; kw < KW; ++kw)
+                    for (int kw = first ? 0 : 1; kw < (first ? 1 : KW); ++kw)
                         for (int c = 0; c < L::kBChunks; ++c) {
                             uint8_t* dst = b_dst + kw * L::kBBytesPerTap + c * kChunkBytes + r * row_bytes;
                             const int ch = nb * BLOCK_N + c * 32;
@@ -162,18 +168,17 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
             }
             umma_commit(tmem_full_bar);
         } else if (warp >= 4) {
-            // ===================== epilogue: TMEM -> fp32 atomics into the weight-gradient layout =====================
+            // ===================== epilogue: TMEM -> this split's slice of the partial buffer =====================
             mbar_wait(tmem_full_bar, 0);
             tcgen05_fence_after();
             const int q = warp - 4;
             const int cs = STACK ? lane : ms * 128 + q * 32 + lane;
-            const int T = p.k * p.k;
+            float* pbase = part + split * p.part_stride;
 #pragma unroll 1
             for (int kw = 0; kw < KW; ++kw) {
                 if (STACK && q == 3) break;                     // duplicate chunk
                 const int t = (STACK ? q : kh) * p.k + kw;
-                const int tt = p.flip ? T - 1 - t : t;
-                float* obase = out + tt * p.stride_t + cs * p.stride_cs + static_cast<long long>(nb) * BLOCK_N * p.stride_cb;
+                float* obase = pbase + (static_cast<long long>(t) * p.Cs + cs) * p.Cb + nb * BLOCK_N;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 32) {
                     uint32_t v[32];
@@ -189,16 +194,46 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(obase + (c + j) * p.stride_cb, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(obase + c + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
                 }
             }
             tcgen05_fence_before();
+        }
+    } else if (warp >= 4) {
+        // a split without work (units not divisible): its slice must still be defined for the reduction
+        const int q = warp - 4;
+        const int cs = STACK ? lane : ms * 128 + q * 32 + lane;
+        float* pbase = part + split * p.part_stride;
+        for (int kw = 0; kw < KW; ++kw) {
+            if (STACK && q == 3) break;
+            const int t = (STACK ? q : kh) * p.k + kw;
+            float* obase = pbase + (static_cast<long long>(t) * p.Cs + cs) * p.Cb + nb * BLOCK_N;
+            for (int c = 0; c < BLOCK_N; c += 4) *reinterpret_cast<float4*>(obase + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L::kTmemCols) : "memory");
+    }
+}
+
+// gw (physical weight-gradient layout, via strides) = sum over splits of part[split][t][cs][cb]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                           WgParams p, int T) {
+    const long long total = static_cast<long long>(T) * p.Cs * p.Cb;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < p.splits; ++s) acc += part[s * p.part_stride + e];
+        const int cb = static_cast<int>(e % p.Cb);
+        const int cs = static_cast<int>((e / p.Cb) % p.Cs);
+        const int t = static_cast<int>(e / (static_cast<long long>(p.Cb) * p.Cs));
+        const int tt = p.flip ? T - 1 - t : t;
+        out[tt * p.stride_t + cs * p.stride_cs + cb * p.stride_cb] = acc;
     }
 }
 
@@ -212,7 +247,7 @@ int pick_bn(int Cb) {
 }
 
 template <int KW, int BLOCK_N, bool STACK>
-int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, const WgParams& p, cudaStream_t st) {
+int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, float* part, const WgParams& p, cudaStream_t st) {
     using L = WgSmem<KW, BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -221,8 +256,14 @@ int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, const Wg
         attr_set = true;
     }
     dim3 grid(STACK ? 1 : p.Cs / 128, p.Cb / BLOCK_N, STACK ? p.splits : p.k * p.splits);
-    wgrad_tc_kernel<KW, BLOCK_N, STACK><<<grid, 256, L::kDynamic, st>>>(ms, mb, out, p);
+    wgrad_tc_kernel<KW, BLOCK_N, STACK><<<grid, 256, L::kDynamic, st>>>(ms, mb, part, p);
     GIFB200_LAUNCH_CHECK("wgrad_tc_kernel");
+    const int T = p.k * p.k;
+    const long long total = static_cast<long long>(T) * p.Cs * p.Cb;
+    int blocks = cdiv(total, 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, out, p, T);
+    GIFB200_LAUNCH_CHECK("wgrad_reduce_kernel");
     return GIFB200_OK;
 }
 
@@ -249,14 +290,33 @@ bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, in
     return true;
 }
 
+static long long wgrad_splits(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, long long* units_out) {
+    int Hs, Ws, Cs, Hb, Wb, Cb;
+    roles(Hi, Wi, Ci, Ho, Wo, Co, mode, Hs, Ws, Cs, Hb, Wb, Cb);
+    const long long units = static_cast<long long>(B) * Hs * Ws / kPix;
+    const int bn = pick_bn(Cb);
+    const bool stack = (Cs == 32 && mode == 0 && k == 3);
+    const long long base_ctas = stack ? (Cb / bn) : static_cast<long long>(Cs / 128) * (Cb / bn) * k;
+    long long splits = (kNumSMs + base_ctas - 1) / base_ctas;
+    if (splits > units) splits = units;
+    if (splits < 1) splits = 1;
+    if (units_out) *units_out = units;
+    return splits;
+}
+
+size_t conv2d_wgrad_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode) {
+    if (!conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode)) return 0;
+    return static_cast<size_t>(wgrad_splits(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, nullptr)) * k * k * Co * Ci * sizeof(float) + 256;
+}
+
 int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                    int k, int mode, int flip, int transposed, cudaStream_t st) {
+                    int k, int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GIFB200_REQUIRE(ws && ws_bytes >= conv2d_wgrad_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_WORKSPACE,
+                    "conv2d_wgrad_tc: workspace too small (see gifb200_conv2d_wgrad_workspace_bytes)");
+    float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
     GIFB200_REQUIRE(conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE,
                     "conv2d_wgrad_tc: unsupported shape");
     GIFB200_REQUIRE(aligned16(x) && aligned16(gy), GIFB200_E_ALIGN, "conv2d_wgrad_tc: x / gy must be 16-byte aligned");
-    const int T = k * k;
-    cudaError_t e = cudaMemsetAsync(gw, 0, sizeof(float) * static_cast<size_t>(T) * Co * Ci, st);
-    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "wgrad memset", cudaGetErrorString(e));
     WgParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.k = k; p.flip = flip;
@@ -274,11 +334,8 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
     p.stride_t = static_cast<long long>(Co) * Ci;
     const int bn = pick_bn(p.Cb);
     const bool stack = (p.Cs == 32 && mode == 0 && k == 3);
-    const long long base_ctas = stack ? (p.Cb / bn) : static_cast<long long>(p.Cs / 128) * (p.Cb / bn) * k;
-    long long splits = (kNumSMs + base_ctas - 1) / base_ctas;
-    if (splits > p.units) splits = p.units;
-    if (splits < 1) splits = 1;
-    p.splits = static_cast<int>(splits);
+    p.splits = static_cast<int>(wgrad_splits(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, nullptr));
+    p.part_stride = static_cast<long long>(k) * k * Co * Ci;
     CUtensorMap ms, mb;
     {
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cs), static_cast<cuuint64_t>(p.Ws), static_cast<cuuint64_t>(p.Hs), static_cast<cuuint64_t>(B)};
@@ -303,10 +360,10 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         int rc = encode_map(&mb, Bg, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     }
-#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false>(ms, mb, gw, p, st)
+#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false>(ms, mb, gw, part, p, st)
     if (stack)
-        return bn == 128 ? launch_wg<3, 128, true>(ms, mb, gw, p, st)
-               : bn == 64 ? launch_wg<3, 64, true>(ms, mb, gw, p, st) : launch_wg<3, 32, true>(ms, mb, gw, p, st);
+        return bn == 128 ? launch_wg<3, 128, true>(ms, mb, gw, part, p, st)
+               : bn == 64 ? launch_wg<3, 64, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true>(ms, mb, gw, part, p, st);
     if (k == 3) return bn == 128 ? GIFB200_WG(3, 128) : bn == 64 ? GIFB200_WG(3, 64) : GIFB200_WG(3, 32);
     return bn == 128 ? GIFB200_WG(1, 128) : bn == 64 ? GIFB200_WG(1, 64) : GIFB200_WG(1, 32);
 #undef GIFB200_WG

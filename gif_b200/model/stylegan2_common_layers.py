@@ -108,6 +108,17 @@ def _conv_mode(kernel_size, stride, padding):
                               "the GIF hot path (supported: stride 1 with 'same' padding, stride 2 without padding)")
 
 
+def _pad_channels_for_tc(x, wt):
+    """tf32 mode: zero-pad the input channels (and the weight's Ci) to a multiple of 32 so that odd-channel layers (the
+    9-channel discriminator stem, the 513-channel minibatch-stddev conv) run on the tcgen05 kernels; values unchanged."""
+    ci = x.shape[-1]
+    if ops.tf32_enabled() and ci % 32 != 0 and wt.shape[1] % 32 == 0:
+        pad = 32 - ci % 32
+        x = F.pad(x, (0, pad))
+        wt = F.pad(wt, (0, pad))
+    return x, wt
+
+
 class EqualConv2d(nn.Module):
     """cl.py:155-190."""
 
@@ -122,7 +133,9 @@ class EqualConv2d(nn.Module):
 
     def forward_nhwc(self, x):
         mode = _conv_mode(self.kernel_size, self.stride, self.padding)
-        y = ops.conv2d(x, ops.prep_weight(self.weight, self.scale), self.kernel_size, mode)
+        wt = ops.prep_weight(self.weight, self.scale)
+        x, wt = _pad_channels_for_tc(x, wt)
+        y = ops.conv2d(x, wt, self.kernel_size, mode)
         if self.bias is not None:
             y = ops.bias_act(y, self.bias, slope=1.0, gain=1.0)
         return y
@@ -411,7 +424,8 @@ class ConvLayer(nn.Sequential):
                     x = ops.upfirdn2d(x, layer.kernel, pad=layer.pad, rt=tf32)
             elif isinstance(layer, EqualConv2d):
                 if layer.kernel_size == 1 and layer.stride == 2:
-                    y = ops.conv2d(x, ops.prep_weight(layer.weight, layer.scale), 1, ops.S1)
+                    xp, wt = _pad_channels_for_tc(x, ops.prep_weight(layer.weight, layer.scale))
+                    y = ops.conv2d(xp, wt, 1, ops.S1)
                     x = y if layer.bias is None else ops.bias_act(y, layer.bias, slope=1.0, gain=1.0)
                 else:
                     x = layer.forward_nhwc(x)

@@ -120,17 +120,19 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
     shape = (k * k, Ci, Co) if transposed else (k * k, Co, Ci)
     gw = torch.empty(shape, dtype=torch.float32, device=x.device)
     impl = WGRAD_IMPL if CONV_IMPL != 1 else 1
-    if lib.gifb200_conv2d_wgrad_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl) > 0:   # tensor-core path
+    nws = lib.gifb200_conv2d_wgrad_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl)
+    if nws > 0:                                                            # tensor-core path
         if not _is_tf32(x):
             x = _round_tf32_raw(x)
         if not _is_tf32(gy):
             gy = _round_tf32_raw(gy)
+    ws = _workspace(nws, x.device)
     prof = PROFILE is not None
     if prof:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     check(lib.gifb200_conv2d_wgrad(ptr(x), ptr(gy), ptr(gw), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip),
-                                   int(transposed), impl, None, 0, stream()), "gifb200_conv2d_wgrad")
+                                   int(transposed), impl, ptr(ws), nws, stream()), "gifb200_conv2d_wgrad")
     if prof:
         ev1.record()
         pix = Hi * Wi if mode == T2 else Ho * Wo

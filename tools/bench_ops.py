@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""Per-operator measurements for the BASELINE.json configs other than the headline step (profiles/ evidence):
+  config 0  ModulatedConv2d(512,512,3) fwd, x (4,512,64,64)                      -> ms, TFLOP/s
+  config 1  StyledGenerator fwd 256^2 bs16                                       -> images/s
+  config 3  FLAME-topology rasterise texture+normal 256^2 bs64 fwd+bwd           -> renders/s, GB/s vs algorithmic bytes
+  3b        north-star layer ModulatedConv2d(128,128,3) x (32,128,256,256) fwd/bwd -> TFLOP/s vs tf32 peak
+  memory-bound kernels (upfirdn2d blur, fused bias/act, ToRGB)                   -> GB/s vs measured HBM peak
+CUDA-event timing on the current stream, >= 3 warm-ups, inputs larger than L2 or L2 flushed between iterations.
+Prints one JSON object per line."""
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+from gif_b200 import ops, rasterize  # noqa: E402
+from gif_b200.flame_synth import synthetic_flame_batch  # noqa: E402
+from gif_b200.model import stylegan2_common_layers as cl  # noqa: E402
+from gif_b200.model.stg2_generator import StyledGenerator  # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAKS = {}
+try:
+    PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+except OSError:
+    pass
+HBM = PEAKS.get("hbm_gbs", 6650.0)
+TF32_BURST = PEAKS.get("bf16_tflops", 1590.0) / 2
+_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warm=3, flush=False):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            _flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def out(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def modconv(ci, co, b, r, tag):
+    m = cl.ModulatedConv2d(ci, co, 3, 512).to(dev)
+    x = torch.randn(b, r, r, ci, device=dev).permute(0, 3, 1, 2)          # NCHW view of channels-last storage
+    st = torch.randn(b, 512, device=dev)
+    flops = 2.0 * b * r * r * ci * co * 9
+    with torch.no_grad():
+        ms = timeit(lambda: m(x, st), flush=True)
+    xg = x.detach().requires_grad_(True)
+
+    def fb():
+        y = m(xg, st)
+        y.backward(torch.ones_like(y))
+    ms_fb = timeit(fb, iters=5, flush=True)
+    # the contraction alone (input already modulated + rounded): gifb200_conv2d through the C ABI
+    xs = ops._round_tf32_raw(torch.randn(b, r, r, ci, device=dev))
+    w = torch.randn(9, co, ci, device=dev) / math.sqrt(9 * ci)
+    ms_k = timeit(lambda: ops._conv_raw(xs, w, 3, ops.S1, False, False, (r, r)), flush=True)
+    gy = ops._round_tf32_raw(torch.randn(b, r, r, co, device=dev))
+    ms_w = timeit(lambda: ops._wgrad_raw(xs, gy, 3, ops.S1, False, False), flush=True)
+    out(bench=tag, shape=[b, ci, r, r, co], module_fwd_ms=ms, module_fwd_tflops=flops / ms / 1e9,
+        module_fwd_bwd_ms=ms_fb, module_fwd_bwd_tflops=3 * flops / ms_fb / 1e9,
+        conv_kernel_ms=ms_k, conv_kernel_tflops=flops / ms_k / 1e9, conv_kernel_frac_of_tf32_burst=flops / ms_k / 1e9 / TF32_BURST,
+        wgrad_kernel_ms=ms_w, wgrad_kernel_tflops=flops / ms_w / 1e9, tf32_peak_burst=TF32_BURST, l2="flushed")
+
+
+def generator_fwd():
+    G = StyledGenerator(embedding_vocab_size=70000, rendered_flame_ascondition=True, normal_maps_as_cond=True).to(dev)
+    cond = torch.rand(16, 6, 256, 256, device=dev) * 2 - 1
+    idx = torch.randint(0, 70000, (16,), device=dev)
+    with torch.no_grad():
+        ms = timeit(lambda: G(cond, step=6, input_indices=idx), iters=5)
+    out(bench="config1_generator_fwd_256_bs16", ms=ms, images_per_s=16 / ms * 1e3, tflops=16 * 105.3 / ms)
+
+
+def raster():
+    b, h, w = 64, 256, 256
+    fv, fc = synthetic_flame_batch(b, h, w, seed=0, device=dev)
+    F = fv.shape[1]
+    fvg = fv.clone().requires_grad_(True)
+    fcg = fc.clone().requires_grad_(True)
+    normals = torch.rand_like(fc).requires_grad_(True)
+    g1 = torch.randn(b, h, w, 3, device=dev)
+
+    def fwd():
+        return rasterize.rasterize(fv, h, w, fc), rasterize.rasterize(fv, h, w, normals.detach())
+
+    def fwd_bwd():
+        d, t, im = rasterize.rasterize(fvg, h, w, fcg)
+        d2, t2, nm = rasterize.rasterize(fvg, h, w, normals)
+        ((im * g1).sum() + (nm * g1).sum()).backward()
+    ms_f = timeit(fwd, flush=True)
+    ms_fb = timeit(fwd_bwd, iters=5, flush=True)
+    # algorithmic bytes per image: texture+normal = two colour rasterisations
+    fwd_bytes = 2 * (2 * F * 36 + h * w * (4 + 4 + 12))                       # faces+colours in, depth/tri/image out
+    bwd_bytes = 2 * (h * w * (12 + 4) + 2 * F * 36 + 2 * F * 36)              # grad+tri in, faces/colours in, 2 grads out
+    out(bench="config3_rasterize_flame_256_bs64", fwd_ms=ms_f, fwd_bwd_ms=ms_fb, renders_per_s_fwd=b / ms_f * 1e3,
+        renders_per_s_fwd_bwd=b / ms_fb * 1e3, fwd_gbs=b * fwd_bytes / ms_f / 1e6, fwd_frac_of_hbm=b * fwd_bytes / ms_f / 1e6 / HBM,
+        fwd_bwd_gbs=b * (fwd_bytes + bwd_bytes) / ms_fb / 1e6, algorithmic_mb_per_image_fwd=fwd_bytes / 1e6, hbm_peak_gbs=HBM,
+        covered_fraction=float((rasterize.rasterize(fv, h, w, fc)[1] >= 0).float().mean()))
+
+
+def memory_bound():
+    x = torch.randn(32, 256, 256, 128, device=dev)
+    k = torch.tensor([1., 3., 3., 1.], device=dev)
+    k = torch.outer(k, k) / 64
+    nbytes = x.numel() * 4
+    ms = timeit(lambda: ops.upfirdn2d(x, k, 1, 1, (2, 2)))
+    ob = 32 * 257 * 257 * 128 * 4
+    out(bench="upfirdn2d_blur_pad22_32x256x256x128", ms=ms, gbs=(nbytes + ob) / ms / 1e6, frac_of_hbm=(nbytes + ob) / ms / 1e6 / HBM)
+    ms = timeit(lambda: ops.upfirdn2d(x, k, 1, 2, (1, 1)))
+    ob = 32 * 128 * 128 * 128 * 4
+    out(bench="upfirdn2d_down2_pad11_32x256x256x128", ms=ms, gbs=(nbytes + ob) / ms / 1e6, frac_of_hbm=(nbytes + ob) / ms / 1e6 / HBM)
+    bias = torch.randn(128, device=dev)
+    d = torch.rand(32, 128, device=dev)
+    add = torch.randn_like(x)
+    ms = timeit(lambda: ops.bias_act(x, bias, 0.2, math.sqrt(2), rowscale=d, add=add))
+    out(bench="bias_act_fused_tail_32x256x256x128", ms=ms, gbs=3 * nbytes / ms / 1e6, frac_of_hbm=3 * nbytes / ms / 1e6 / HBM)
+    ms = timeit(lambda: ops.bias_act(x, bias, 0.2, math.sqrt(2)))
+    out(bench="bias_act_plain_32x256x256x128", ms=ms, gbs=2 * nbytes / ms / 1e6, frac_of_hbm=2 * nbytes / ms / 1e6 / HBM)
+    ws = torch.randn(32, 3, 128, device=dev)
+    ms = timeit(lambda: ops.torgb(x, ws))
+    out(bench="torgb_32x256x256x128", ms=ms, gbs=(nbytes + 32 * 65536 * 12) / ms / 1e6, frac_of_hbm=(nbytes + 32 * 65536 * 12) / ms / 1e6 / HBM)
+    s = torch.rand(32, 128, device=dev)
+    ms = timeit(lambda: ops.chan_scale(x, s, True))
+    out(bench="chan_scale_32x256x256x128", ms=ms, gbs=2 * nbytes / ms / 1e6, frac_of_hbm=2 * nbytes / ms / 1e6 / HBM)
+
+
+if __name__ == "__main__":
+    ops.set_precision("tf32")
+    which = sys.argv[1:] or ["northstar", "config0", "generator", "raster", "memory"]
+    if "northstar" in which:
+        modconv(128, 128, 32, 256, "northstar_modconv_128_128_256x256_bs32")
+    if "config0" in which:
+        modconv(512, 512, 4, 64, "config0_modconv_512_512_64x64_bs4")
+    if "generator" in which:
+        generator_fwd()
+    if "raster" in which:
+        raster()
+    if "memory" in which:
+        memory_bound()
