@@ -33,6 +33,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                         // fp32 elements = 128 bytes = one swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kMaxTaps = 9;
+constexpr int kTcThreads = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per TMEM lane quarter)
 
 struct TcParams {
     int B, Hs, Ws;          // site grid per image
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // The smem ring and its phase bits run continuously across tiles; the TMEM accumulator is double buffered so the
 // epilogue of tile i overlaps the main loop of tile i+1 of the same CTA (and the second resident CTA fills the rest).
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                          const __grid_constant__ CUtensorMap map_b,
                                                          float* __restrict__ y, const TcParams p, const int mtiles,
                                                          const int total_tiles) {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], kTcThreads - 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -169,7 +170,10 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int q = warp - 4;                      // TMEM lane quarter this warp may access
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access (warp id mod 4)
+        const int half = (warp - 4) >> 2;            // which half of the tile's columns this warp drains
+        constexpr int kColsPerWarp = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+        const bool active = BLOCK_N >= 64 || half == 0;
         const int r = q * 32 + lane;                 // tile row == TMEM lane
         const int w_in = r % p.wt, h_in = (r / p.wt) % p.ht, n_in = r / (p.wt * p.ht);
         int local = 0;
@@ -183,15 +187,16 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
             const int ty = m % p.tiles_y; m /= p.tiles_y;
             const int n = m * p.nt + n_in;
             const int Y = (ty * p.ht + h_in) * p.oys + p.phase_oy0[phase], X = (tx * p.wt + w_in) * p.oxs + p.phase_ox0[phase];
-            const bool ok = n < p.B && Y < p.Ho && X < p.Wo;
-            float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N;
+            const bool ok = active && n < p.B && Y < p.Ho && X < p.Wo;
+            const int col0 = (BLOCK_N >= 64 ? half * kColsPerWarp : 0);
+            float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N + col0;
             const int buf = local & 1;
             mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            for (int c = 0; active && c < kColsPerWarp; c += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + c;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + col0 + c;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -204,14 +209,11 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + c + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                        __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 8) st_global_v8(dst + c + j, v + j);   // 32-byte stores: whole sectors
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(&tmem_empty_bar[buf]);       // 128 arrivals release the buffer to the MMA issuer
+            mbar_arrive(&tmem_empty_bar[buf]);       // all 256 epilogue threads arrive -> buffer released to the MMA issuer
         }
     }
     __syncthreads();
@@ -263,7 +265,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* y, const TcParam
     const long long total = static_cast<long long>(mtiles) * (p.Co / BLOCK_N) * p.nphase;
     if (total > 2147483647LL) return fail(GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
     const int grid = total < 2 * kNumSMs ? static_cast<int>(total) : 2 * kNumSMs;   // persistent: <= 2 CTAs per SM
-    conv_tc_kernel<BLOCK_N><<<grid, 256, L::kDynamic, st>>>(ma, mb, y, p, mtiles, static_cast<int>(total));
+    conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, L::kDynamic, st>>>(ma, mb, y, p, mtiles, static_cast<int>(total));
     GIFB200_LAUNCH_CHECK("conv_tc_kernel");
     return GIFB200_OK;
 }

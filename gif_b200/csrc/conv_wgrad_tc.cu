@@ -194,10 +194,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(obase + c + j) =
-                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                        __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 8) st_global_v8(obase + c + j, v + j);
                 }
             }
             tcgen05_fence_before();

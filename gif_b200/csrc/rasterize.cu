@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* __restrict__ fv, 
             } else {
                 const int pos = offset[bin] + atomicAdd(count + bin, 1);   // count was re-zeroed: acts as cursor
                 if (pos < (b + 1) * capacity) list[pos] = f;               // capacity = list slots per image
-                else *overflow = 1;
+                else overflow[b] = 1;
             }
         }
 }
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int* __restrict__ count,
         if (threadIdx.x == 0) carry += warp_tot[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0 && carry > (static_cast<int>(blockIdx.x) + 1) * capacity) *overflow = 1;
+    if (threadIdx.x == 0 && carry > (static_cast<int>(blockIdx.x) + 1) * capacity) overflow[blockIdx.x] = 1;
 }
 
 struct Frag {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) raster_kernel(const float* __restrict__ f
     float best_z = in_img ? depth[pix] : 0.f;
     int best_f = 0x7fffffff;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-    const bool brute = *overflow != 0;
+    const bool brute = overflow[b] != 0;     // this image's lists did not fit: walk all F triangles (still exact)
     const int n = brute ? g.F : count[gbin];
     const int* lst = list + (brute ? 0 : offset[gbin]);
     const float fpx = static_cast<float>(px), fpy = static_cast<float>(py);
@@ -276,16 +276,16 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 using namespace gifb200;
 
-// workspace layout: [count: B*nbins ints][offset: B*nbins ints][overflow flag (padded to 256 B)][list: B*capacity ints]
-static int list_capacity(int F) {   // list slots per image; avg. bins per visible triangle is ~2
-    const long long cap = static_cast<long long>(F) * 4 + 1024;
+// workspace layout: [count: B*nbins ints][offset: B*nbins ints][overflow flags: B ints (padded)][list: B*capacity ints]
+static int list_capacity(int F) {   // list slots per image; a FLAME render at 256^2 needs ~1.2 F, allow 8 F
+    const long long cap = static_cast<long long>(F) * 8 + 1024;
     return static_cast<int>(cap > 0x3fffffffLL ? 0x3fffffffLL : cap);
 }
 
 extern "C" size_t gifb200_rasterize_workspace_bytes(int B, int F, int h, int w) {
     if (B <= 0 || h <= 0 || w <= 0 || F < 0) return 0;
     const size_t nb = static_cast<size_t>(B) * ((h + BIN - 1) / BIN) * ((w + BIN - 1) / BIN);
-    return align_up(nb * 4, 256) * 2 + 256 + static_cast<size_t>(list_capacity(F)) * 4 * B;
+    return align_up(nb * 4, 256) * 2 + align_up(static_cast<size_t>(B) * 4, 256) + static_cast<size_t>(list_capacity(F)) * 4 * B;
 }
 
 extern "C" int gifb200_rasterize_fwd(const float* face_vertices, const float* face_colors, float* depth,
@@ -305,10 +305,10 @@ extern "C" int gifb200_rasterize_fwd(const float* face_vertices, const float* fa
     int* count = reinterpret_cast<int*>(ws);
     int* offset = reinterpret_cast<int*>(ws + align_up(nb * 4, 256));
     int* overflow = reinterpret_cast<int*>(ws + align_up(nb * 4, 256) * 2);
-    int* list = overflow + 64;
+    int* list = reinterpret_cast<int*>(reinterpret_cast<char*>(overflow) + align_up(static_cast<size_t>(B) * 4, 256));
     const int capacity = list_capacity(F);
     GIFB200_REQUIRE(static_cast<long long>(B) * capacity < 0x7fffffffLL, GIFB200_E_SHAPE, "rasterize: B*F too large");
-    cudaError_t e = cudaMemsetAsync(ws, 0, align_up(nb * 4, 256) * 2 + 256, st);
+    cudaError_t e = cudaMemsetAsync(ws, 0, align_up(nb * 4, 256) * 2 + align_up(static_cast<size_t>(B) * 4, 256), st);
     if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "rasterize memset", cudaGetErrorString(e));
     const long long ntri = static_cast<long long>(B) * F;
     bin_kernel<0><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);

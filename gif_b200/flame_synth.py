@@ -3,8 +3,11 @@
 The FLAME model itself (generic_model.pkl, texture space) is licence-gated and absent from the reference tree, so
 "random FLAME params" drive a FLAME-*shaped* linear decoder on the real FLAME topology (V=5023, F=9976; template from
 my_utils/photometric_optimization/data/head_template_mesh.obj, stored as tests/golden/flame_template.npz):
-    verts = T + sum_j beta_j S_j,  beta ~ N(0,1) (B,150),  S ~ N(0,(2 mm)^2)
-followed by the reference's camera path: a random head rotation (cf. plots/generate_random_samples.py:107-108),
+    verts = T + sum_j beta_j S_j,  beta ~ N(0,1) (B,150)
+with a SMOOTH basis S_j(v) = a * d_j * cos(2 pi f_j . T_v + phi_j) (|f_j| <= 8 cycles/m, a = 0.5 mm, i.e. ~4 mm rms total
+displacement, comparable to FLAME's shape+expression range).  (SURVEY 8d suggested i.i.d. per-vertex noise N(0,(2 mm)^2)
+per coefficient; that sums to 24 mm rms of *uncorrelated* vertex noise, which crumples the mesh into image-sized slivers
+(mean bbox 1800 px^2 at 256^2) and no longer resembles a FLAME render, so it is not used.)  It is followed by the reference's camera path: a random head rotation (cf. plots/generate_random_samples.py:107-108),
 util.batch_orth_proj (util.py:73-83) + the y/z flip of gif_helper.py:26-27, and the pixel mapping of
 visibility.py:38-40 (x*w/2+w/2, y*h/2+h/2, z-min(z)+1).
 """
@@ -31,7 +34,12 @@ def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
     """-> face_vertices (B,F,3,3) fp32 in pixel space, face_colors (B,F,3,3) in [0,1]."""
     tmpl, faces = flame_topology()
     g = torch.Generator().manual_seed(1234 + seed)
-    basis = torch.randn(150, tmpl.shape[0] * 3, generator=torch.Generator().manual_seed(7)) * 0.002
+    gb = torch.Generator().manual_seed(7)
+    freq = (torch.rand(150, 3, generator=gb) * 2 - 1) * 8.0
+    phase = torch.rand(150, 1, generator=gb) * (2 * math.pi)
+    dirs = torch.nn.functional.normalize(torch.randn(150, 3, generator=gb), dim=1)
+    wave = torch.cos(2 * math.pi * (freq @ tmpl.t()) + phase)                     # (150, V)
+    basis = (0.0005 * wave[:, :, None] * dirs[:, None, :]).reshape(150, -1)       # (150, V*3)
     beta = torch.randn(batch, 150, generator=g)
     verts = tmpl[None] + (beta @ basis).reshape(batch, -1, 3)
     yaw = (torch.rand(batch, generator=g) * 2 - 1) * (math.pi / 8)

@@ -74,8 +74,8 @@ def test_flame_batch_matches_oracle(cuda):
     d2, t2, o2 = RO.oracle_rasterize_colors(fv.numpy(), colors.numpy(), 256, 256)
     assert np.array_equal(t, t2) and np.array_equal(d, d2) and np.array_equal(o, o2)
     assert (t >= 0).mean() > 0.2
-    # overflow fallback: 3000 image-sized triangles per image overflow the per-image list capacity (4F+1024 slots for
-    # 1024 bins each) -> brute-force path, still bit-exact
+    # overflow fallback: 3000 image-sized triangles per image overflow the per-image list capacity (8F+1024 slots;
+    # each triangle touches up to 64 bins) -> brute-force path for that image, still bit-exact
     rng = np.random.default_rng(1)
     big = np.zeros((1, 3000, 3, 3), np.float32)
     big[..., :2] = rng.uniform(-20, 84, (1, 3000, 3, 2))
