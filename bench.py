@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--impl", default="gif_b200", choices=["gif_b200", "reference"])
     ap.add_argument("--no-ppl", action="store_true", help="drop the path-length regulariser from the G step")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ppl-extra", action="store_true", help="skip the additional measurement without the PPL term")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
@@ -277,6 +278,24 @@ def main():
         e2e = {"value": world * B * args.steps / (ms_e / 1000.0), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 8}
 
+    extra_no_ppl = None
+    if trainer.ppl is not None and not args.no_ppl_extra:
+        # the same step without the (parity-unpinned, never enabled in a shipped reference config) path-length regulariser
+        trainer.ppl = None
+        trainer._graphs = None
+        try:
+            if not args.no_graph:
+                trainer.capture(B, RES)
+                trainer.iteration = 14
+                run(2, False)
+            else:
+                trainer.iteration = 13
+                run(3, False)
+            ms_np = timed(args.steps, False)
+            extra_no_ppl = {"value": world * B * args.steps / (ms_np / 1000.0), "unit": "images/sec",
+                            "ms_per_step": ms_np / args.steps}
+        except Exception as e:
+            extra_no_ppl = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -304,15 +323,27 @@ def main():
             pass
         bf16 = peaks.get("bf16_tflops_sustained")
         peak = bf16 / 2 if bf16 else 1400.0 / 2
-        ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        ach_all = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         ns = [(a.elapsed_time(b), f) for a, b, f, tag in prof if tag == "northstar"]
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        # dominant kernel instance: conv_tc_kernel<128> on the north-star layer (B,128,256,256)->128, 3x3:
+        # algorithmic FLOPs per launch = 2*9*128*128 per output pixel * 32*256*256 pixels = 618.5 GFLOP
+        ach = (sum(f for _, f in ns) / (sum(t for t, _ in ns) * 1e-3) / 1e12) if ns else ach_all
+        traffic = None
+        try:    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["conv_tc_northstar_dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<128> (tcgen05 kind::tf32 implicit GEMM) on the north-star layer "
+                                             "ModulatedConv2d 128->128 3x3 @256x256, batch 32",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "algorithmic_flops_per_launch": 2.0 * 9 * 128 * 128 * 32 * 256 * 256,
+                "algorithmic_hbm_bytes_per_launch": 2 * 32 * 256 * 256 * 128 * 4 + 9 * 128 * 128 * 4,
+                "launches_of_this_shape": len(ns), "avg_launch_ms": (sum(t for t, _ in ns) / len(ns)) if ns else None,
+                "all_tensor_core_conv_launches": {"achieved": ach_all, "frac": ach_all / peak},
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate; no tf32 entry"
                                 " in the file)") if bf16 else "fallback 1.4 PFLOP/s sustained bf16 / 2",
                 "launches": len(prof), "kernel_ms_per_step": tot_ms / prof_steps,
-                "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note,
-                "northstar_layer_tflops": (sum(f for _, f in ns) / (sum(t for t, _ in ns) * 1e-3) / 1e12) if ns else None}
+                "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note}
     cb = None
     if not args.no_cpu_baseline:
         cb = cpu_arm(1, 0)
@@ -323,7 +354,8 @@ def main():
                                    "Adam, EMA, R1 every 16th iteration" + ("" if args.no_ppl else ", path-length reg every iteration"),
                        "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}", "cuda_graph": graph_note,
                        "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
-            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb}
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb,
+            "same_step_without_path_length_reg": extra_no_ppl}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -46,6 +46,20 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 
+// fused convolution epilogue: y = lrelu(acc + bias[o]) * gain (optionally tf32-rounded); act == 0: identity
+struct ConvEpilogue {
+    int act;
+    const float* bias;
+    float slope, gain;
+    int rtf32;
+};
+__device__ __forceinline__ float apply_epilogue(const ConvEpilogue& e, float acc, int o) {
+    if (!e.act) return acc;
+    float t = acc + (e.bias ? __ldg(e.bias + o) : 0.f);
+    t = (t > 0.f ? t : t * e.slope) * e.gain;
+    return e.rtf32 ? round_tf32(t) : t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

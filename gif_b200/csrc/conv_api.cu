@@ -3,14 +3,14 @@
 
 namespace gifb200 {
 int conv2d_simt(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
-                int mode, int flip, int transposed, cudaStream_t st);
+                int mode, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st);
 int conv2d_wgrad_simt(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
                       int k, int mode, int flip, int transposed, cudaStream_t st);
 // conv_tc.cu
 bool conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
 size_t conv2d_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, int transposed);
 int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
-              int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st);
+              int mode, int flip, int transposed, const ConvEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
 // conv_wgrad_tc.cu
 bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
 size_t conv2d_wgrad_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
@@ -28,15 +28,17 @@ extern "C" size_t gifb200_conv2d_workspace_bytes(int B, int Hi, int Wi, int Ci, 
 }
 
 extern "C" int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
-                              int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,
-                              size_t workspace_bytes, gifb200_stream_t stream) {
+                              int Co, int k, int mode, int flip, int transposed, int impl, int act, const float* bias,
+                              float slope, float gain, int round_tf32, void* workspace, size_t workspace_bytes,
+                              gifb200_stream_t stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ConvEpilogue epi{act, bias, slope, gain, round_tf32};
     GIFB200_REQUIRE(impl >= 0 && impl <= 2, GIFB200_E_SHAPE, "conv2d: impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
     const bool tc_ok = conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (impl == 2 && !tc_ok) return fail(GIFB200_E_SHAPE, "conv2d: shape not supported by the tcgen05 path");
     if (impl != 1 && tc_ok)
-        return conv2d_tc(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, workspace, workspace_bytes, st);
-    return conv2d_simt(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, st);
+        return conv2d_tc(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, epi, workspace, workspace_bytes, st);
+    return conv2d_simt(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, epi, st);
 }
 
 // > 0 exactly when the tcgen05 path will be taken (split-K partial sums live in the workspace)

@@ -12,6 +12,7 @@ struct ConvParams {
     int B, Hi, Wi, Ci, Ho, Wo, Co, k, flip;
     long long M;  // number of output pixels this launch produces (B*Ho*Wo, or B*(Wo+Ho-1) in strip mode)
     int strip;    // 1: only the last output row and the last output column (border strip of a T2 convolution)
+    ConvEpilogue epi;
 };
 
 // m-th output pixel of the launch -> (b, yo, xo)
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int o = n0 + tn + j;
-            if (o < p.Co) yrow[o] = acc[i][j];
+            if (o < p.Co) yrow[o] = apply_epilogue(p.epi, acc[i][j], o);
         }
     }
 }
@@ -223,26 +224,28 @@ static int check_conv_shape(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int C
 }
 
 static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
-                            int Co, int k, int mode, int flip, int transposed, int strip, cudaStream_t st);
+                            int Co, int k, int mode, int flip, int transposed, int strip, const ConvEpilogue& epi,
+                            cudaStream_t st);
 
 int conv2d_simt(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
-                int mode, int flip, int transposed, cudaStream_t st) {
-    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, 0, st);
+                int mode, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st) {
+    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, 0, epi, st);
 }
 
 // last output row + last output column of a T2 convolution (the part the tcgen05 phase kernels do not cover)
 int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                      int k, int flip, int transposed, cudaStream_t st) {
-    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, 2, flip, transposed, 1, st);
+                      int k, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st) {
+    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, 2, flip, transposed, 1, epi, st);
 }
 
 static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
-                            int Co, int k, int mode, int flip, int transposed, int strip, cudaStream_t st) {
+                            int Co, int k, int mode, int flip, int transposed, int strip, const ConvEpilogue& epi,
+                            cudaStream_t st) {
     int rc = check_conv_shape(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (rc != GIFB200_OK) return rc;
     if (B == 0) return GIFB200_OK;
     ConvParams p{B, Hi, Wi, Ci, Ho, Wo, Co, k, flip,
-                 strip ? static_cast<long long>(B) * (Wo + Ho - 1) : static_cast<long long>(B) * Ho * Wo, strip};
+                 strip ? static_cast<long long>(B) * (Wo + Ho - 1) : static_cast<long long>(B) * Ho * Wo, strip, epi};
     const long long mb = (p.M + BM - 1) / BM;
     GIFB200_REQUIRE(mb <= 2147483647LL && cdiv(Co, BN) <= 65535, GIFB200_E_SHAPE, "conv2d: grid too large");
     dim3 grid(static_cast<unsigned>(mb), cdiv(Co, BN));

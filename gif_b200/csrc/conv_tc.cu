@@ -24,7 +24,7 @@
 namespace gifb200 {
 
 int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                      int k, int flip, int transposed, cudaStream_t st);
+                      int k, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st);
 
 namespace {
 
@@ -50,6 +50,7 @@ struct TcParams {
     int tap_dx[4][kMaxTaps];    // input column = site_x + tap_dx        (S2: column in the W/2 space)
     int tap_par[4][kMaxTaps];   // S2: W parity plane
     int in_sy;
+    ConvEpilogue epi;
 };
 
 template <int BLOCK_N>
@@ -208,6 +209,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ok) {
+                    if (p.epi.act) {
+                        const int o0 = nblk * BLOCK_N + col0 + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(apply_epilogue(p.epi, __uint_as_float(v[j]), o0 + j));
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) st_global_v8(dst + c + j, v + j);   // 32-byte stores: whole sectors
                 }
@@ -289,7 +295,7 @@ size_t conv2d_tc_workspace_bytes(int, int, int, int Ci, int, int, int Co, int k,
 }
 
 int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
-              int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st) {
+              int mode, int flip, int transposed, const ConvEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st) {
     GIFB200_REQUIRE(conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE, "conv2d_tc: unsupported shape");
     GIFB200_REQUIRE(ws && ws_bytes >= conv2d_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, transposed),
                     GIFB200_E_WORKSPACE, "conv2d_tc: workspace too small (see gifb200_conv2d_workspace_bytes)");
@@ -309,7 +315,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         }
         cudaEventRecord(ev_fork, st);
         cudaStreamWaitEvent(aux, ev_fork, 0);
-        int rcs = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, aux);
+        int rcs = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, epi, aux);
         cudaEventRecord(ev_join, aux);
         if (rcs != GIFB200_OK) { cudaStreamWaitEvent(st, ev_join, 0); return rcs; }
     }
@@ -322,7 +328,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.B = B; p.Ci = Ci; p.Co = Co; p.Ho = Ho; p.Wo = Wo;
+    p.B = B; p.Ci = Ci; p.Co = Co; p.Ho = Ho; p.Wo = Wo; p.epi = epi;
     site_grid(Hi, Wi, Ho, Wo, mode, p.Hs, p.Ws);
     p.wt = p.Ws < 128 ? p.Ws : 128;
     p.ht = (128 / p.wt) < p.Hs ? (128 / p.wt) : p.Hs;

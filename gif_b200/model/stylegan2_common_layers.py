@@ -135,10 +135,9 @@ class EqualConv2d(nn.Module):
         mode = _conv_mode(self.kernel_size, self.stride, self.padding)
         wt = ops.prep_weight(self.weight, self.scale)
         x, wt = _pad_channels_for_tc(x, wt)
-        y = ops.conv2d(x, wt, self.kernel_size, mode)
         if self.bias is not None:
-            y = ops.bias_act(y, self.bias, slope=1.0, gain=1.0)
-        return y
+            return ops.conv2d_bias_act(x, wt, self.bias, self.kernel_size, mode, slope=1.0, gain=1.0)
+        return ops.conv2d(x, wt, self.kernel_size, mode)
 
     def forward(self, input):
         return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input)))
@@ -295,10 +294,8 @@ class NoiseInjection(nn.Module):
             b2 = F.pad(b2, (0, up32(c2n) - c2n))
             w4 = F.pad(w4, (0, up32(c2n) - c2n))
         rt = ops.tf32_enabled()
-        h = ops.conv2d(noise, w0, 3, ops.S1)
-        h = ops.bias_act(h, b0, slope=0.0, gain=1.0, rt=rt)               # + bias, ReLU
-        h = ops.conv2d(h, w2, 3, ops.S1)
-        h = ops.bias_act(h, b2, slope=0.0, gain=1.0, rt=rt)
+        h = ops.conv2d_bias_act(noise, w0, b0, 3, ops.S1, slope=0.0, gain=1.0, rt=rt)   # conv + bias + ReLU, one kernel
+        h = ops.conv2d_bias_act(h, w2, b2, 3, ops.S1, slope=0.0, gain=1.0, rt=rt)
         h = ops.conv2d(h, w4, 3, ops.S1)
         return h, c4.bias
 
@@ -411,31 +408,32 @@ class ConvLayer(nn.Sequential):
         super().__init__(*layers)
 
     def forward_nhwc(self, x, rt_out=False):
-        """Channels-last fast path used by ResBlock / Discriminator (same arithmetic as the Sequential)."""
+        """Channels-last fast path used by ResBlock / Discriminator (same arithmetic as the Sequential): the blur is one
+        upfirdn2d pass, and convolution + bias + leaky-ReLU*sqrt(2) is ONE kernel (fused epilogue)."""
         tf32 = ops.tf32_enabled()
-        for layer in self:
-            if isinstance(layer, Blur):
-                conv = self[1]
-                if conv.kernel_size == 1:
-                    # blur(pad 1,1) then 1x1 stride-2 conv == FIR evaluated only at the even output sites
-                    # (upfirdn2d down=2), then a stride-1 1x1 conv: 4x fewer FIR outputs (cl.py:765-771,:776-786)
-                    x = ops.upfirdn2d(x, layer.kernel, down=2, pad=layer.pad, rt=tf32)
-                else:
-                    x = ops.upfirdn2d(x, layer.kernel, pad=layer.pad, rt=tf32)
-            elif isinstance(layer, EqualConv2d):
-                if layer.kernel_size == 1 and layer.stride == 2:
-                    xp, wt = _pad_channels_for_tc(x, ops.prep_weight(layer.weight, layer.scale))
-                    y = ops.conv2d(xp, wt, 1, ops.S1)
-                    x = y if layer.bias is None else ops.bias_act(y, layer.bias, slope=1.0, gain=1.0)
-                else:
-                    x = layer.forward_nhwc(x)
-            elif isinstance(layer, FusedLeakyReLU):
-                x = ops.bias_act(x, layer.bias, layer.negative_slope, layer.scale, rt=rt_out and tf32)
-            elif isinstance(layer, ScaledLeakyReLU):
-                x = ops.bias_act(x, None, layer.negative_slope, math.sqrt(2), rt=rt_out and tf32)
+        layers = list(self)
+        i = 0
+        if isinstance(layers[0], Blur):
+            blur, conv = layers[0], layers[1]
+            if conv.kernel_size == 1:
+                # blur(pad 1,1) then 1x1 stride-2 conv == FIR evaluated only at the even output sites
+                # (upfirdn2d down=2), then a stride-1 1x1 conv: 4x fewer FIR outputs (cl.py:765-771,:776-786)
+                x = ops.upfirdn2d(x, blur.kernel, down=2, pad=blur.pad, rt=tf32)
             else:
-                raise TypeError(type(layer))
-        return x
+                x = ops.upfirdn2d(x, blur.kernel, pad=blur.pad, rt=tf32)
+            i = 1
+        conv = layers[i]
+        act = layers[i + 1] if i + 1 < len(layers) else None
+        k = conv.kernel_size
+        mode = ops.S1 if (k == 1 and conv.stride == 2) else _conv_mode(k, conv.stride, conv.padding)
+        xp, wt = _pad_channels_for_tc(x, ops.prep_weight(conv.weight, conv.scale))
+        if isinstance(act, FusedLeakyReLU):
+            return ops.conv2d_bias_act(xp, wt, act.bias, k, mode, act.negative_slope, act.scale, rt=rt_out and tf32)
+        if isinstance(act, ScaledLeakyReLU):
+            return ops.conv2d_bias_act(xp, wt, None, k, mode, act.negative_slope, math.sqrt(2), rt=rt_out and tf32)
+        if conv.bias is not None:
+            return ops.conv2d_bias_act(xp, wt, conv.bias, k, mode, slope=1.0, gain=1.0)
+        return ops.conv2d(xp, wt, k, mode)
 
     def forward(self, input):
         return ops.to_nchw_view(self.forward_nhwc(ops.to_nhwc(input)))

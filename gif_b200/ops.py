@@ -87,7 +87,8 @@ def conv_out_size(hi, k, mode):
     return 2 * (hi - 1) + k
 
 
-def _conv_raw(x, w, k, mode, flip, transposed, out_hw):
+def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None):
+    """epilogue: None (plain accumulator) or (bias_flat or None, slope, gain, round_tf32) fused into the kernel."""
     require_cuda(x, w)
     B, Hi, Wi, Ci = x.shape
     T, R, S = w.shape
@@ -103,8 +104,14 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw):
     if prof:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    if epilogue is None:
+        act, bias, slope, gain, rt = 0, None, 1.0, 1.0, 0
+    else:
+        bias, slope, gain, rt = epilogue
+        act = 1
     check(lib.gifb200_conv2d(ptr(x), ptr(w), ptr(y), B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, int(flip), int(transposed),
-                             CONV_IMPL, ptr(ws), nws, stream()), "gifb200_conv2d")
+                             CONV_IMPL, act, ptr(bias), float(slope), float(gain), int(rt), ptr(ws), nws, stream()),
+          "gifb200_conv2d")
     if prof:
         ev1.record()
         pix = Hi * Wi if mode == T2 else Ho * Wo                    # algorithmic MACs: taps * Ci * Co per site
@@ -186,6 +193,43 @@ class _ConvWgrad(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             ggy = _Conv.apply(x, ggw, k, mode, flip, transposed, tuple(gy.shape[1:3]))
         return gx, ggy, None, None, None, None
+
+
+class _ConvBiasAct(torch.autograd.Function):
+    """y = lrelu(conv(x; w) + bias, slope) * gain in ONE kernel (fused epilogue of gifb200_conv2d): ConvLayer =
+    EqualConv2d -> FusedLeakyReLU (cl.py:752-799), nn.Conv2d(+ReLU) of NoiseInjection (cl.py:405-414).  The backward is
+    composed of the differentiable primitives (activation backward from the saved OUTPUT, adjoint conv, wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, k, mode, slope, gain, rt, out_hw):
+        x, w = _c(x), _c(w)
+        bias_flat = None if bias is None else _c(bias.reshape(-1))
+        y, x_used = _conv_raw(x, w, k, mode, False, False, out_hw, (bias_flat, slope, gain, rt))
+        ctx.save_for_backward(x_used, w, y)
+        ctx.cfg = (k, mode, slope, gain, tuple(x.shape[1:3]), _is_tf32(x_used), None if bias is None else bias.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        k, mode, slope, gain, in_hw, x_tf32, bias_shape = ctx.cfg
+        _tag(x, x_tf32)
+        gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _Conv.apply(gt, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
+        if ctx.needs_input_grad[1]:
+            gw = _ConvWgrad.apply(x, gt, k, mode, False, False)
+        if bias_shape is not None and ctx.needs_input_grad[2]:
+            gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def conv2d_bias_act(x, w, bias, k, mode=S1, slope=0.2, gain=math.sqrt(2.0), rt=False):
+    """Fused conv + bias + leaky-ReLU*gain (slope=1, gain=1: plain bias add; slope=0: ReLU)."""
+    hi, wi = x.shape[1:3]
+    out_hw = (conv_out_size(hi, k, mode), conv_out_size(wi, k, mode))
+    return _tag(_ConvBiasAct.apply(x, w, bias, k, mode, float(slope), float(gain), bool(rt), out_hw), rt)
 
 
 def conv2d(x, w, k, mode=S1, flip=False, transposed=False):

@@ -59,12 +59,15 @@ long long gifb200_launch_count(void);
  *
  * impl: 0 = auto (tcgen05 tensor-core path when the shape qualifies, else SIMT), 1 = force SIMT fp32,
  *       2 = force tcgen05 (kind::tf32, fp32 accumulate; returns GIFB200_E_SHAPE if the shape does not qualify).
- * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL). */
+ * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL).
+ * Fused epilogue (ConvLayer = EqualConv2d -> FusedLeakyReLU, cl.py:752-799; nn.Conv2d + ReLU of NoiseInjection):
+ *     y = lrelu(acc + bias[o], slope) * gain, optionally rounded to tf32;  act == 0 writes the plain accumulator
+ *     (bias / slope / gain / round_tf32 ignored). */
 size_t gifb200_conv2d_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
                                       int transposed, int impl);
 int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                   int k, int mode, int flip, int transposed, int impl, void* workspace, size_t workspace_bytes,
-                   gifb200_stream_t stream);
+                   int k, int mode, int flip, int transposed, int impl, int act, const float* bias, float slope,
+                   float gain, int round_tf32, void* workspace, size_t workspace_bytes, gifb200_stream_t stream);
 
 /* Weight gradient of gifb200_conv2d for the same (mode, flip, transposed), written in the PHYSICAL layout of w
  * (so it can be accumulated into / compared with the weight buffer directly):

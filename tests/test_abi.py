@@ -41,7 +41,7 @@ def test_error_codes_without_gpu():
     from gif_b200 import _lib
     rc = _lib.lib.gifb200_upfirdn2d(None, None, None, 1, 4, 4, 4, 4, 4, 9, 9, 1, 1, 0, 0, 0, 0, None)
     assert rc == -1 and b"8x8" in _lib.lib.gifb200_last_error()
-    rc = _lib.lib.gifb200_conv2d(None, None, None, 1, 8, 8, 4, 8, 8, 4, 5, 0, 0, 0, 1, None, 0, None)
+    rc = _lib.lib.gifb200_conv2d(None, None, None, 1, 8, 8, 4, 8, 8, 4, 5, 0, 0, 0, 1, 0, None, 1.0, 1.0, 0, None, 0, None)
     assert rc == -1
     assert _lib.lib.gifb200_rasterize_workspace_bytes(2, 100, 64, 64) > 0
 
