@@ -241,7 +241,7 @@ def main():
             trainer.iteration = 14
             run(2, False)                      # one replay of each graph before timing
             barrier()
-            graph_note = "2 CUDA graphs per rank (iteration with / without R1), replayed"
+            graph_note = "3 CUDA graphs per iteration (cut at the two gradient all-reduces) x 2 variants (with / without R1), replayed"
         except Exception as e:                 # capture is an optimisation of the launch path, never a different compute path
             trainer._graphs = None
             graph_note = f"capture failed, eager launches: {type(e).__name__}: {str(e)[:200]}"
@@ -260,10 +260,11 @@ def main():
     ops.PROFILE = None
     clocks = sampler.stop() if rank == 0 else None
     prof_note = "per-launch CUDA events inside the timed region"
-    if use_graph and rank == 0:
+    if use_graph:
         # graph replays cannot carry per-launch events: time the same kernels in a separate eager pass of the same steps
+        # (all ranks run it -- it contains the gradient all-reduces -- only rank 0 records events)
         saved, trainer._graphs = trainer._graphs, None
-        ops.PROFILE = []
+        ops.PROFILE = [] if rank == 0 else None
         timed(min(args.steps, 4), False)
         prof = ops.PROFILE
         ops.PROFILE = None

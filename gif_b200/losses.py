@@ -46,6 +46,10 @@ class PathLengthRegularizor:
         g = generator.module if hasattr(generator, "module") else generator
         w = g.z_to_w(g.img_embdng(input_indices))
         fake = _synth_from_w(g, w, cond, step)
+        return self.path_length_from(fake, w, pl_noise)
+
+    def path_length_from(self, fake, w, pl_noise=None):
+        """The penalty for images ``fake`` already synthesised (with a graph) from the latent ``w``."""
         if pl_noise is None:
             pl_noise = torch.randn(fake.shape, device=fake.device)
         pl_noise = pl_noise / np.sqrt(np.prod(fake.shape))                       # losses.py:114

@@ -4,8 +4,11 @@ rule), Adam with the reference's hyper-parameters (train.py:365-382), EMA of the
 
 Differences from the reference, all deliberate:
   * nn.DataParallel -> FlatGradAllReducer (one all-reduce per net per step);
-  * the fake images of the D step are generated under no_grad (the reference builds, then discards, a G graph because
-    gen_in1 requires grad, train.py:140,152,160 -- the detached result is identical);
+  * ONE generator forward per iteration instead of two (three with PPL).  The reference calls the generator in the D step
+    (train.py:157, result detached at :160) and again in the G step (train.py:197) with the same inputs while the
+    generator's weights are unchanged (only D is updated in between), so both calls return bit-identical images; the
+    path-length term differentiates the same images w.r.t. the same w.  Here the forward runs once with a graph: the D
+    step consumes ``fake.detach()``, the G step (and PPL) reuse the graph.  Same arithmetic, one third of the G forwards;
   * data loading / FID / checkpoints are outside the hot path.
 """
 import copy
@@ -59,46 +62,65 @@ class GifTrainer:
 
     # ------------------------------------------------------------------------------------------- CUDA graphs
     def capture(self, batch, resolution):
-        """Capture the whole iteration (D step + G step, both optimiser updates, EMA, the gradient all-reduces) into two
-        CUDA graphs -- one for the iterations with the R1 penalty, one for those without -- so that a step is two
-        cudaGraphLaunch calls instead of ~2000 kernel launches issued from Python.  Call after a few eager warm-up
-        iterations (optimiser state and workspaces must exist).  ``train_iteration`` then copies its inputs into the
-        static buffers and replays."""
+        """Capture the iteration into CUDA graphs so that a step is a handful of cudaGraphLaunch calls instead of ~2000
+        kernel launches issued from Python.  The iteration is cut at the two gradient exchanges, which stay OUTSIDE the
+        graphs (eager ``torch.distributed`` all-reduce on the same stream):
+            seg 1: generator forward, D forward x2 (+R1), D backward      | all-reduce D grads
+            seg 2: D Adam step, D forward on fake, G (and PPL) backward   | all-reduce G grads
+            seg 3: G Adam step, EMA
+        x 2 variants (iteration with / without the R1 penalty).  Call after a few eager warm-up iterations (optimiser
+        state and workspaces must exist).  ``train_iteration`` then copies its inputs into the static buffers and replays."""
+        from . import _lib
         dev = self.device
         self._static = (torch.zeros(batch, 3, resolution, resolution, device=dev),
                         torch.zeros(batch, 6, resolution, resolution, device=dev),
                         torch.zeros(batch, dtype=torch.long, device=dev))
-        from . import _lib
-        graphs = {}
-        pool = None
+        graphs, pool = {}, None
         self.graph_launches = {}
         torch.cuda.synchronize()
         for with_r1 in (True, False):
-            g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g, pool=pool):
-                out = self._iteration_body(*self._static, with_r1=with_r1)
-            self.graph_launches[with_r1] = _lib.launch_count() - n0        # gif_b200 kernel nodes per replay
-            pool = g.pool()
-            graphs[with_r1] = (g, out)
+            segs, state = [], {}
+            for seg in (self._seg1, self._seg2, self._seg3):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg(state, *self._static, with_r1)
+                pool = g.pool()
+                segs.append(g)
+            self.graph_launches[with_r1] = _lib.launch_count() - n0      # gif_b200 kernel nodes per replayed iteration
+            graphs[with_r1] = (segs, (state["d_loss"], state["g_loss"]))
         self._graphs = graphs
 
     def train_iteration(self, real_image, flm_rndr, input_indices):
-        """real_image (B,3,R,R) in [-1,1], flm_rndr (B,6,R,R) in [-1,1], input_indices (B,) int64 -- device tensors.
-        Returns (d_loss, g_loss) as 0-d device tensors."""
+        """real_image (B,3,R,R) in [-1,1], flm_rndr (B,6,R,R) in [-1,1], input_indices (B,) int64 -- device tensors (or
+        pinned host tensors when CUDA graphs are active).  Returns (d_loss, g_loss) as 0-d device tensors."""
         with_r1 = (self.iteration + 1) % self.r1_every == 0                       # train.py:145
         self.iteration += 1
         if self._graphs is not None:
             self.replayed_launches = getattr(self, "replayed_launches", 0) + self.graph_launches[with_r1]
             for dst, src in zip(self._static, (real_image, flm_rndr, input_indices)):
                 dst.copy_(src, non_blocking=True)
-            g, out = self._graphs[with_r1]
-            g.replay()
+            (g1, g2, g3), out = self._graphs[with_r1]
+            g1.replay()
+            self.d_reducer.all_reduce_mean()
+            g2.replay()
+            self.g_reducer.all_reduce_mean()
+            g3.replay()
             return out
-        return self._iteration_body(real_image, flm_rndr, input_indices, with_r1)
+        state = {}
+        self._seg1(state, real_image, flm_rndr, input_indices, with_r1)
+        self.d_reducer.all_reduce_mean()
+        self._seg2(state, real_image, flm_rndr, input_indices, with_r1)
+        self.g_reducer.all_reduce_mean()
+        self._seg3(state, real_image, flm_rndr, input_indices, with_r1)
+        return state["d_loss"], state["g_loss"]
 
-    def _iteration_body(self, real_image, flm_rndr, input_indices, with_r1):
+    def _seg1(self, st, real_image, flm_rndr, input_indices, with_r1):
         G, D, step = self.generator, self.discriminator, self.step_idx
+        # ------------------------------------------------ shared generator forward (train.py:157 == train.py:197)
+        requires_grad(G, True)
+        w = G.z_to_w(G.img_embdng(input_indices))                                # gen.py:275
+        fake = losses._synth_from_w(G, w, flm_rndr, step)                         # the graph is reused by the G step
         # ------------------------------------------------ D step (train.py:82-178)
         requires_grad(D, True)
         self.d_reducer.zero()
@@ -107,26 +129,28 @@ class GifTrainer:
         real_loss = F.softplus(-real_scores).mean()
         if with_r1:                                                               # train.py:145-149
             real_loss = real_loss + losses.grad_penalty_loss([real_image], real_scores, step=None).mean()
-        with torch.no_grad():
-            fake = G(flm_rndr, None, step=step, alpha=1, input_indices=input_indices)[0]
-        fake_scores, _ = D([fake], condition=flm_rndr, step=step, alpha=1)
+        fake_scores, _ = D([fake.detach()], condition=flm_rndr, step=step, alpha=1)   # train.py:160-170
         d_loss = real_loss + F.softplus(fake_scores).mean()
         d_loss.backward()
-        self.d_reducer.all_reduce_mean()
+        st.update(w=w, fake=fake, d_loss=d_loss.detach())
+
+    def _seg2(self, st, real_image, flm_rndr, input_indices, with_r1):
+        G, D, step = self.generator, self.discriminator, self.step_idx
         self.d_optimizer.step()
         # ------------------------------------------------ G step (train.py:181-252)
-        requires_grad(G, True)
         requires_grad(D, False)
         self.g_reducer.zero()
-        fake = G(flm_rndr, None, step=step, alpha=1, input_indices=input_indices)[0]
-        predict, _ = D([fake], condition=flm_rndr, step=step, alpha=1)
+        predict, _ = D([st["fake"]], condition=flm_rndr, step=step, alpha=1)      # the UPDATED discriminator (train.py:200)
         g_loss = F.softplus(-predict).mean()
-        if self.ppl is not None:
-            g_loss = g_loss + 2 * self.ppl.path_length_reg(G, step=step, alpha=1, input_indices=input_indices,
-                                                           cond=flm_rndr)       # train.py:205-208
+        if self.ppl is not None:                                                  # train.py:205-208, weight 2
+            g_loss = g_loss + 2 * self.ppl.path_length_from(st["fake"], st["w"])
         g_loss.backward()
-        self.g_reducer.all_reduce_mean()
+        st["g_loss"] = g_loss.detach()
+        st.pop("fake")
+        st.pop("w")
+
+    def _seg3(self, st, real_image, flm_rndr, input_indices, with_r1):
+        G = self.generator
         self.g_optimizer.step()
         accumulate(self.g_running, G, decay=0.5 ** (32 / (10 * 1000)))            # train.py:250
         requires_grad(G, False)
-        return d_loss.detach(), g_loss.detach()
