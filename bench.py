@@ -43,6 +43,18 @@ METRIC = "G+D train step images/sec @256x256 bs32/GPU"
 RES, BATCH, VOCAB = 256, 32, 70_000
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,12 +174,17 @@ def reference_main(args):
             "config": {"workload": "train_step_256_bs32 (CPU arm: bounded sample at batch 1, see cpu_baseline.sample)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
+    # Libraries (NCCL prints its version banner) write to stdout: keep fd 1 for the ONE JSON line, send the rest to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_main(args)
     from gif_b200 import _lib, ops
@@ -276,8 +293,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         ms_e = timed(args.steps, True)
-        e2e = {"value": world * B * args.steps / (ms_e / 1000.0), "unit": "images/sec", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 8}
+        e2e = {"value": world * B * args.steps / (ms_e / 1000.0), "unit": "images/sec", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 8 * world}
 
     extra_no_ppl = None
     if trainer.ppl is not None and not args.no_ppl_extra:
@@ -357,7 +374,7 @@ def main():
                        "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb,
             "same_step_without_path_length_reg": extra_no_ppl}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

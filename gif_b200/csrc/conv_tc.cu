@@ -306,7 +306,9 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     // (event fork/join: stream-ordered, capturable in CUDA graphs, no host synchronisation).
     static cudaStream_t aux = nullptr;
     static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (mode == 2) {
+    // forking costs two cross-stream event edges: only worth it when the tensor-core part is long enough to hide the strip
+    const bool fork = mode == 2 && static_cast<long long>(B) * Hi * Wi >= 32768;
+    if (fork) {
         if (!aux) {
             if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -395,9 +397,11 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     if (bn == 128) rc = launch<128>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else if (bn == 64) rc = launch<64>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else rc = launch<32>(ma, mb, y, p, static_cast<int>(mtiles), st);
-    if (mode == 2) {
+    if (fork) {
         cudaError_t e = cudaStreamWaitEvent(st, ev_join, 0);      // join: later work on `st` sees the strip
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "conv2d_tc: join", cudaGetErrorString(e));
+    } else if (mode == 2 && rc == GIFB200_OK) {
+        rc = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, epi, st);
     }
     return rc;
 }

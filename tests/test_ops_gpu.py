@@ -203,3 +203,22 @@ def test_modulated_conv_config1(cuda, fp32_mode):
     e = np.abs(s - g["config1_sample"]).max() / float(g["config1_absmax"])
     assert e < 5e-5, e
     assert abs(tot - float(g["config1_sum"])) / (float(g["config1_absmax"]) * math.sqrt(y.numel())) < 1e-4
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", [(32, 512, 8192, False, True), (512, 8192, 32, True, False), (32, 8192, 512, False, False),
+                                         (3, 16, 24, False, True), (70, 33, 1500, False, True)])
+def test_sgemm_shapes_incl_split_k(cuda, m, n, k, ta, tb):
+    """EqualLinear GEMMs incl. the split-K path (8192 -> 512 discriminator head) and ragged edges, fwd + both gradients."""
+    from gif_b200 import ops
+    a = gu.randn((k, m) if ta else (m, k), 1)
+    b = gu.randn((n, k) if tb else (k, n), 2)
+    ag, bg = a.to(cuda).requires_grad_(True), b.to(cuda).requires_grad_(True)
+    c = ops.matmul(ag, bg, ta, tb, alpha=0.5)
+    ao, bo = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    co = 0.5 * (ao.t() if ta else ao) @ (bo.t() if tb else bo)
+    close(c, co, 2e-5, "C")
+    g = gu.randn((m, n), 3)
+    ga, gb = torch.autograd.grad(c, [ag, bg], g.to(cuda))
+    gao, gbo = torch.autograd.grad(co, [ao, bo], g.double())
+    close(ga, gao, 2e-5, "dA")
+    close(gb, gbo, 2e-5, "dB")
