@@ -43,20 +43,29 @@ SIGNATURES = {
     "gifb200_cond_down": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gifb200_rasterize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gifb200_rasterize_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "gifb200_render_shade": (_i, [_p] * 9 + [_i] * 5 + [_p]),
     "gifb200_rasterize_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
 }
 
 
-def _load():
-    if not os.path.isfile(LIB_PATH):
-        from . import build as _build  # nvcc cross-compiles without a GPU
-        _build.build()
-    lib = ctypes.CDLL(LIB_PATH)
+def _bind(path):
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
     return lib
+
+
+def _load():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_gifb200_build", os.path.join(_HERE, "build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
+    # incremental (content-hash stamps): a no-op when the library is current, a rebuild when the sources changed
+    # (nvcc cross-compiles without a GPU).  A library that still lacks a declared symbol afterwards fails the import.
+    _build.build()
+    return _bind(LIB_PATH)
 
 
 lib = _load()

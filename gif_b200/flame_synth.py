@@ -30,16 +30,34 @@ def flame_topology():
     return _cache["t"]
 
 
-def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
-    """-> face_vertices (B,F,3,3) fp32 in pixel space, face_colors (B,F,3,3) in [0,1]."""
+def flame_uv():
+    """(uvcoords (5118,2), uvfaces (9976,3)) of the FLAME template."""
+    z = np.load(_TEMPLATE)
+    return torch.from_numpy(z["uvcoords"].astype(np.float32)), torch.from_numpy(z["uvfaces"].astype(np.int64))
+
+
+def synthetic_flame_params(batch, seed=0):
+    """World-space vertices (B,V,3), weak-perspective cameras (B,3), albedo textures (B,3,256,256) in 0..255 and SH lights
+    (B,9,3) for the render benchmark: the smooth FLAME-shaped decoder below + random pose / camera / smooth random albedo."""
     tmpl, faces = flame_topology()
-    g = torch.Generator().manual_seed(1234 + seed)
+    g = torch.Generator().manual_seed(4321 + seed)
+    verts = _decode(batch, g, tmpl)
+    cam = torch.cat([torch.rand(batch, 1, generator=g) * 3 + 7, (torch.rand(batch, 2, generator=g) * 2 - 1) * 0.02], 1)
+    low = torch.rand(batch, 3, 8, 8, generator=g) * 255
+    albedo = torch.nn.functional.interpolate(low, size=(256, 256), mode="bilinear", align_corners=False)
+    lights = torch.zeros(batch, 9, 3)
+    lights[:, 0] = 3.0 + 0.3 * torch.randn(batch, 3, generator=g)
+    lights[:, 1:] = 0.3 * torch.randn(batch, 8, 3, generator=g)
+    return verts, cam, albedo, lights
+
+
+def _decode(batch, g, tmpl):
     gb = torch.Generator().manual_seed(7)
     freq = (torch.rand(150, 3, generator=gb) * 2 - 1) * 8.0
     phase = torch.rand(150, 1, generator=gb) * (2 * math.pi)
     dirs = torch.nn.functional.normalize(torch.randn(150, 3, generator=gb), dim=1)
-    wave = torch.cos(2 * math.pi * (freq @ tmpl.t()) + phase)                     # (150, V)
-    basis = (0.0005 * wave[:, :, None] * dirs[:, None, :]).reshape(150, -1)       # (150, V*3)
+    wave = torch.cos(2 * math.pi * (freq @ tmpl.t()) + phase)
+    basis = (0.0005 * wave[:, :, None] * dirs[:, None, :]).reshape(150, -1)
     beta = torch.randn(batch, 150, generator=g)
     verts = tmpl[None] + (beta @ basis).reshape(batch, -1, 3)
     yaw = (torch.rand(batch, generator=g) * 2 - 1) * (math.pi / 8)
@@ -48,7 +66,14 @@ def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
     zero, one = torch.zeros_like(cy), torch.ones_like(cy)
     ry = torch.stack([cy, zero, sy, zero, one, zero, -sy, zero, cy], -1).reshape(batch, 3, 3)
     rx = torch.stack([one, zero, zero, zero, cp, -sp, zero, sp, cp], -1).reshape(batch, 3, 3)
-    verts = verts @ (rx @ ry).transpose(1, 2)
+    return verts @ (rx @ ry).transpose(1, 2)
+
+
+def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
+    """-> face_vertices (B,F,3,3) fp32 in pixel space, face_colors (B,F,3,3) in [0,1]."""
+    tmpl, faces = flame_topology()
+    g = torch.Generator().manual_seed(1234 + seed)
+    verts = _decode(batch, g, tmpl)
     cam = torch.cat([torch.rand(batch, 1, generator=g) * 3 + 7, (torch.rand(batch, 2, generator=g) * 2 - 1) * 0.02], 1)
     proj = torch.cat([verts[..., :2] + cam[:, None, 1:], verts[..., 2:]], -1) * cam[:, None, 0:1]   # batch_orth_proj
     proj[..., 1:] = -proj[..., 1:]                                                                   # gif_helper.py:27

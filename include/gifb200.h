@@ -163,6 +163,18 @@ int gifb200_rasterize_bwd(const float* face_vertices, const float* face_colors, 
                           const float* g_bary, const float* g_img, const float* g_depth, float* g_face_vertices,
                           float* g_face_colors, int B, int F, int h, int w, gifb200_stream_t stream);
 
+/* Fused shading epilogue of the FLAME conditioning render: from the rasteriser's (triangle, bary) buffers to the textured
+ * image tex (B,h,w,3) = albedo(uv) * SH-shading(normal) * alpha, the normal image nrm (B,h,w,3), and the quantised
+ * 6-channel condition map cond (B,h,w,6) in [-1,1] (each output may be NULL).
+ * Replaces the attribute interpolation of Pytorch3dRasterizer.forward (photometric_optimization/renderer.py:69-84),
+ * Renderer.forward's grid_sample / add_SHlight / composition (renderer.py:152-221), Renderer.render_normal (:291-305),
+ * OverLayViz.get_rendered_mesh's quantisation (my_utils/visualize_flame_overlay.py:29-31) and the consumer's mapping
+ * to [-1,1] (loss_functions/losses.py:213-214).  face_uv (F,3,2) grid coordinates in [-1,1] (shared by the batch),
+ * face_normals (B,F,3,3) world-space vertex normals per face corner, albedo (B,3,T,T), sh (B,9,3). */
+int gifb200_render_shade(const int32_t* triangle, const float* bary, const float* face_uv, const float* face_normals,
+                         const float* albedo, const float* sh, float* tex, float* nrm, float* cond, int B, int F, int h,
+                         int w, int T, gifb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,10 +40,10 @@ def body():
 
 
 def flame():
-    v, f = RO.load_obj_vf(REF + "/my_utils/photometric_optimization/data/head_template_mesh.obj")
-    assert v.shape == (5023, 3) and f.shape == (9976, 3)
+    v, f, vt, ft = RO.load_obj_vf(REF + "/my_utils/photometric_optimization/data/head_template_mesh.obj", with_uv=True)
+    assert v.shape == (5023, 3) and f.shape == (9976, 3) and vt.shape == (5118, 2) and ft.shape == (9976, 3)
     np.savez_compressed(os.path.join(gu.GOLDEN_DIR, "flame_template.npz"), vertices=v.astype(np.float32),
-                        faces=f.astype(np.int32))
+                        faces=f.astype(np.int32), uvcoords=vt.astype(np.float32), uvfaces=ft.astype(np.int32))
 
 
 def cases():
@@ -65,7 +65,37 @@ def cases():
     np.savez_compressed(os.path.join(gu.GOLDEN_DIR, "raster_cases.npz"), **out)
 
 
+def render_pieces():
+    """Pins oracle/render_oracle.py's vertex_normals / batch_orth_proj / add_sh_light to the reference's own functions
+    (my_utils/photometric_optimization/util.py:73-83,156-189; renderer.py:207-221, called unbound on a stand-in object that
+    only carries the constant_factor buffer of renderer.py:119-126)."""
+    import types
+    import torch
+    from oracle import ref_import, render_oracle as RD
+    ref_import.load()
+    from my_utils.photometric_optimization import renderer as ref_renderer, util as ref_util
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "flame_template.npz"))
+    faces = torch.from_numpy(z["faces"].astype(np.int64))
+    g = torch.Generator().manual_seed(5)
+    verts = torch.from_numpy(z["vertices"])[None].repeat(2, 1, 1) + 0.003 * torch.randn(2, 5023, 3, generator=g)
+    cam = torch.tensor([[8.0, 0.01, -0.02], [9.5, -0.015, 0.005]])
+    n_ref = ref_util.vertex_normals(verts, faces[None].expand(2, -1, -1))
+    n_or = RD.vertex_normals(verts, faces)
+    assert (n_ref - n_or).abs().max() < 1e-6
+    p_ref = ref_util.batch_orth_proj(verts, cam)
+    assert (p_ref - RD.batch_orth_proj(verts, cam)).abs().max() < 1e-6
+    nimg = torch.randn(2, 3, 8, 8, generator=g)
+    shc = torch.randn(2, 9, 3, generator=g)
+    fake_self = types.SimpleNamespace(constant_factor=RD.SH_CONST.clone())
+    s_ref = ref_renderer.Renderer.add_SHlight(fake_self, nimg, shc)
+    assert (s_ref - RD.add_sh_light(nimg, shc)).abs().max() < 1e-5
+    np.savez_compressed(os.path.join(gu.GOLDEN_DIR, "render_pieces.npz"), verts=verts.numpy(), cam=cam.numpy(),
+                        normals=n_ref.numpy(), proj=p_ref.numpy(), nimg=nimg.numpy(), sh=shc.numpy(), shading=s_ref.numpy())
+    print("render pieces: vertex_normals / batch_orth_proj / add_SHlight match the reference")
+
+
 if __name__ == "__main__":
     body()
     flame()
     cases()
+    render_pieces()

@@ -98,8 +98,8 @@ def get_visibility(vertices, faces, h, w, rasterize=oracle_rasterize):
     return vis
 
 
-def load_obj_vf(path):
-    vs, fs = [], []
+def load_obj_vf(path, with_uv=False):
+    vs, fs, vts, fts = [], [], [], []
     with open(path) as f:
         for line in f:
             p = line.split()
@@ -107,8 +107,15 @@ def load_obj_vf(path):
                 continue
             if p[0] == "v":
                 vs.append([float(x) for x in p[1:]])
+            elif p[0] == "vt":
+                vts.append([float(x) for x in p[1:3]])
             elif p[0] == "f":
                 fs.append([int(x.split("/")[0]) - 1 for x in p[1:4]])
+                if with_uv:
+                    fts.append([int(x.split("/")[1]) - 1 for x in p[1:4]])
+    if with_uv:
+        return (np.asarray(vs, np.float64), np.asarray(fs, np.int64), np.asarray(vts, np.float64),
+                np.asarray(fts, np.int64))
     return np.asarray(vs, np.float64), np.asarray(fs, np.int64)
 
 

@@ -118,6 +118,20 @@ def raster():
         covered_fraction=float((rasterize.rasterize(fv, h, w, fc)[1] >= 0).float().mean()))
 
 
+def render():
+    """FLAME params -> 6-channel condition map (rasterise + fused shading), bs64 @256^2."""
+    from gif_b200.flame_synth import flame_topology, flame_uv, synthetic_flame_params
+    from gif_b200.render import FlameRenderer
+    b, S = 64, 256
+    verts, cam, alb, lights = (t.to(dev) for t in synthetic_flame_params(b, seed=0))
+    _, faces = flame_topology()
+    uv, uvf = flame_uv()
+    R = FlameRenderer(faces, uv, uvf, image_size=S).to(dev)
+    ms = timeit(lambda: R.render_tex_and_normal(verts, cam, alb, lights), flush=True)
+    out(bench="config3_flame_condition_render_256_bs64", ms=ms, renders_per_s=b / ms * 1e3,
+        note="projection + vertex normals (torch glue on 5023 vertices) + rasterise + fused shade -> tex, normal, cond maps")
+
+
 def memory_bound():
     x = torch.randn(32, 256, 256, 128, device=dev)
     k = torch.tensor([1., 3., 3., 1.], device=dev)
@@ -155,5 +169,6 @@ if __name__ == "__main__":
         generator_fwd()
     if "raster" in which:
         raster()
+        render()
     if "memory" in which:
         memory_bound()
