@@ -27,6 +27,7 @@ SIGNATURES = {
     "gifb200_conv2d_workspace_bytes": (_sz, [_i] * 11),
     "gifb200_conv2d": (_i, [_p, _p, _p] + [_i] * 13 + [_p, _f, _f, _i, _p, _sz, _p]),
     "gifb200_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 10),
+    "gifb200_conv2d_wgrad_path": (_i, [_i] * 10),
     "gifb200_conv2d_wgrad": (_i, [_p, _p, _p] + [_i] * 12 + [_p, _sz, _p]),
     "gifb200_upfirdn2d": (_i, [_p, _p, _p] + [_i] * 14 + [_p]),
     "gifb200_bias_act": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p]),

@@ -42,14 +42,16 @@ def tf32_enabled():
 
 
 def _tag(t, rounded):
-    """Marks a tensor whose values are exactly representable in tf32 (so a tcgen05 consumer needs no rounding pass)."""
+    """Marks a tensor whose values are exactly representable in tf32 (so a tcgen05 consumer needs no rounding pass).
+    The mark records the tensor's version counter: autograd's in-place gradient accumulation (``buffer += grad``) keeps the
+    Python object -- and its attributes -- but bumps the version, which invalidates the mark."""
     if rounded:
-        t._gifb200_tf32 = True
+        t._gifb200_tf32 = t._version
     return t
 
 
 def _is_tf32(t):
-    return getattr(t, "_gifb200_tf32", False)
+    return getattr(t, "_gifb200_tf32", None) == t._version
 
 
 def _round_tf32_raw(x):
@@ -128,7 +130,7 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
     gw = torch.empty(shape, dtype=torch.float32, device=x.device)
     impl = WGRAD_IMPL if CONV_IMPL != 1 else 1
     nws = lib.gifb200_conv2d_wgrad_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl)
-    if nws > 0:                                                            # tensor-core path
+    if lib.gifb200_conv2d_wgrad_path(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl) == 2:   # MN-major tensor-core path
         if not _is_tf32(x):
             x = _round_tf32_raw(x)
         if not _is_tf32(gy):
