@@ -16,19 +16,9 @@ bool conv2d_wgrad_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, in
 size_t conv2d_wgrad_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode);
 int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
                     int k, int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st);
-// conv_wgrad_k.cu (K-major variant on pixel-contiguous copies; stride-1 convolutions with W % 32 == 0)
-bool conv2d_wgrad_k_supported(int B, int H, int W, int Ci, int Co, int k);
-size_t conv2d_wgrad_k_workspace_bytes(int B, int H, int W, int Ci, int Co, int k, int have_xT, int have_gyT);
-int conv2d_wgrad_k(const float* x, const float* gy, const float* xT, const float* gyT, float* gw, int B, int H, int W, int Ci,
-                   int Co, int k, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st);
 }  // namespace gifb200
 
 using namespace gifb200;
-
-// impl 3 = the K-major variant (explicit; impl 0 picks it for stride-1 shapes it supports)
-static bool use_wgrad_k(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, int impl) {
-    return (impl == 0 || impl == 3) && mode == 0 && Hi == Ho && Wi == Wo && conv2d_wgrad_k_supported(B, Hi, Wi, Ci, Co, k);
-}
 
 extern "C" size_t gifb200_conv2d_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
                                                  int transposed, int impl) {
@@ -55,27 +45,19 @@ extern "C" int gifb200_conv2d(const float* x, const float* w, float* y, int B, i
 extern "C" size_t gifb200_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
                                                        int mode, int impl) {
     if (impl == 1) return 0;
-    if (use_wgrad_k(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl))
-        return conv2d_wgrad_k_workspace_bytes(B, Hi, Wi, Ci, Co, k, 0, 0);
-    if (impl == 3) return 0;
     return conv2d_wgrad_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
 }
 
 extern "C" int gifb200_conv2d_wgrad_path(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, int impl) {
     if (impl == 1) return 1;
-    if (use_wgrad_k(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl)) return 3;
-    if (impl != 3 && conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode)) return 2;
+    if (conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode)) return 2;
     return impl == 0 ? 1 : 0;
 }
 
 extern "C" int gifb200_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho,
                                     int Wo, int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,
                                     size_t workspace_bytes, gifb200_stream_t stream) {
-    GIFB200_REQUIRE(impl >= 0 && impl <= 3, GIFB200_E_SHAPE, "conv2d_wgrad: impl must be 0, 1, 2 or 3");
-    if (use_wgrad_k(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl))
-        return conv2d_wgrad_k(x, gy, nullptr, nullptr, gw, B, Hi, Wi, Ci, Co, k, flip, transposed, workspace, workspace_bytes,
-                              static_cast<cudaStream_t>(stream));
-    if (impl == 3) return fail(GIFB200_E_SHAPE, "conv2d_wgrad: shape not supported by the K-major tcgen05 path");
+    GIFB200_REQUIRE(impl >= 0 && impl <= 2, GIFB200_E_SHAPE, "conv2d_wgrad: impl must be 0, 1 or 2");
     const bool tc_ok = conv2d_wgrad_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (impl == 2 && !tc_ok) return fail(GIFB200_E_SHAPE, "conv2d_wgrad: shape not supported by the tcgen05 path");
     if (impl != 1 && tc_ok)

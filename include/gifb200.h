@@ -74,13 +74,11 @@ int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int 
  *     gW[t,o,i] = sum_{b,pixels} gy[b,p_out,o] * x[b,p_in(p_out,t),i]   (p_in as in the mode's formula above)
  * x is the conv input (B,Hi,Wi,Ci), gy the conv output gradient (B,Ho,Wo,Co).  gw is OVERWRITTEN.
  * Replaces autograd's conv weight gradient for the reference modules listed above.
- * impl: 0 auto, 1 SIMT fp32, 2 tcgen05 on the channels-last operands (MN-major, half MMA rate for 32-bit types),
- *       3 tcgen05 K-major on pixel-contiguous tf32 copies built in the workspace (stride-1, W % 32 == 0, Co % 128 == 0);
- *       auto prefers 3, then 2, then 1. */
+ * impl: 0 auto, 1 SIMT fp32, 2 tcgen05 on the channels-last operands (MN-major tiles). */
 size_t gifb200_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
                                             int impl);
-/* which kernel gifb200_conv2d_wgrad will run for this shape / impl request: 1, 2 or 3 as above (0: request not possible).
- * Paths 2 needs tf32-rounded operands (see round_tf32 below); path 3 rounds while building its copies; path 1 is exact. */
+/* which kernel gifb200_conv2d_wgrad will run for this shape / impl request: 1 or 2 as above (0: request not possible).
+ * Path 2 needs tf32-rounded operands (see round_tf32 below); path 1 is exact fp32. */
 int gifb200_conv2d_wgrad_path(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, int impl);
 int gifb200_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
                          int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,

@@ -85,31 +85,6 @@ WG_CASES = [
 ]
 
 
-WGK_CASES = [(1, 32, 64, 128, 128, 3), (2, 64, 64, 32, 256, 3), (2, 32, 32, 96, 128, 1), (3, 8, 32, 64, 128, 3),
-             (1, 128, 128, 128, 128, 3), (5, 4, 32, 32, 128, 3)]
-
-
-@pytest.mark.parametrize("B,H,W,Ci,Co,k", WGK_CASES)
-@pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
-def test_wgrad_kmajor_matches_simt(cuda, B, H, W, Ci, Co, k, flip, transposed):
-    """impl 3: K-major tcgen05 weight gradient on pixel-contiguous tf32 copies (built by the library's transpose kernel)."""
-    from gif_b200 import ops
-    g = torch.Generator(device="cuda").manual_seed(B * 31 + H + Ci)
-    x = round_tf32(torch.randn(B, H, W, Ci, device=cuda, generator=g))
-    gy = round_tf32(torch.randn(B, H, W, Co, device=cuda, generator=g))
-    res = []
-    for impl in (3, 1):
-        old = (ops.CONV_IMPL, ops.WGRAD_IMPL)
-        ops.CONV_IMPL, ops.WGRAD_IMPL = (0, 3) if impl == 3 else (1, 1)
-        try:
-            res.append(ops._wgrad_raw(x, gy, k, 0, flip, transposed))
-        finally:
-            ops.CONV_IMPL, ops.WGRAD_IMPL = old
-    torch.cuda.synchronize()
-    e = gu.rel_err(res[0].cpu().numpy(), res[1].cpu().numpy())
-    assert e < 5e-5, e
-
-
 @pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", WG_CASES)
 @pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
 def test_wgrad_tc_matches_simt(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transposed):
