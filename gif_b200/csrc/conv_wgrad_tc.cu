@@ -17,6 +17,8 @@
 // so the four 32-row chunks of the A tile hold the SAME 32 channels of S at three different row shifts (dy = +1, 0, -1;
 // the 4th chunk is a duplicate) -- chunk kh then accumulates kernel row kh, the KW shifted Bg tiles give the kernel
 // columns, and ONE CTA produces all 9 taps (no kh split).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace gifb200 {
@@ -30,6 +32,7 @@ constexpr int kAChunks = 4;                    // M = 128 small channels
 struct WgParams {
     int B, Hs, Ws, Cs, Hb, Wb, Cb;
     int k, pad, s2, flip;
+    int halo_bo;            // HALO: put the row phase of the tap's start address into the descriptor's base_offset field
     int pw;                 // pixels per TMA row load (min(Ws, 32)); rows per stage = 32 / pw
     long long units;        // number of 32-pixel units in the small grid
     int splits;
@@ -37,8 +40,9 @@ struct WgParams {
     long long part_stride;   // floats per split in the partial buffer: T * Cs_total * Cb (layout [split][t][cs][cb])
 };
 
-__device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                               uint32_t base_offset = 0) {
+    uint64_t d = static_cast<uint64_t>(base_offset & 7) << 49;   // swizzle-phase of a start address inside an atom
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;       // between 32-channel (MN) chunks
     d |= static_cast<uint64_t>(512 >> 4) << 32;             // between 4-pixel (K) swizzle atoms
@@ -47,28 +51,37 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_add
     return d;
 }
 
-template <int KW, int BLOCK_N>
+constexpr int kHaloRows = kPix + 2;                 // 34 pixel rows: the 32 of the stage + one on each side
+constexpr int kHaloChunkBytes = 4608;               // 34 * 128 B padded to a multiple of the 512 B swizzle atom
+
+// HALO (stride-1 layers with Ws >= 32): the KW shifted big-tensor tiles of a stage overlap in all but 2 pixel rows, so the
+// stage holds ONE (32 + 2)-row tile per 32-channel chunk and tap kw addresses it at row offset kw (start address + kw*128 B).
+// 35 KB instead of 64 KB per stage -> a 5-deep ring instead of 3 and 8 instead of 16 TMA issues.
+template <int KW, int BLOCK_N, bool HALO = false>
 struct WgSmem {
     static constexpr int kBChunks = BLOCK_N / 32;
     static constexpr int kABytes = kAChunks * kChunkBytes;
     static constexpr int kBBytesPerTap = kBChunks * kChunkBytes;
-    static constexpr int kStageBytes = kABytes + KW * kBBytesPerTap;
-    static constexpr int kBarrierOffset = kWgStages * kStageBytes;
+    static constexpr int kStages = HALO ? 5 : kWgStages;
+    static constexpr int kStageBytes = HALO ? kABytes + kBChunks * kHaloChunkBytes : kABytes + KW * kBBytesPerTap;
+    static constexpr int kTxBytes = HALO ? kABytes + kBChunks * kHaloRows * 128 : kStageBytes;
+    static constexpr int kBarrierOffset = (kStages * kStageBytes + 1023) / 1024 * 1024;
     static constexpr int kDynamic = kBarrierOffset + 128 + 1024;
     static constexpr int kTmemCols = (KW * BLOCK_N <= 32) ? 32 : (KW * BLOCK_N <= 64) ? 64 : (KW * BLOCK_N <= 128) ? 128
                                      : (KW * BLOCK_N <= 256) ? 256 : 512;
 };
 
-template <int KW, int BLOCK_N, bool STACK>
+template <int KW, int BLOCK_N, bool STACK, bool HALO>
 __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
                                                           const __grid_constant__ CUtensorMap map_b,
                                                           float* __restrict__ part, const WgParams p) {
-    using L = WgSmem<KW, BLOCK_N>;
+    using L = WgSmem<KW, BLOCK_N, HALO>;
+    constexpr int kNStages = L::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
-    uint64_t* empty_bar = full_bar + kWgStages;
-    uint64_t* tmem_full_bar = empty_bar + kWgStages;
+    uint64_t* empty_bar = full_bar + kNStages;
+    uint64_t* tmem_full_bar = empty_bar + kNStages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kWgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kNStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -100,7 +113,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (iters > 0) {
-        if ((warp == 0 || warp == 3) && lane == 0) {
+        if ((warp == 0 || (warp == 3 && !HALO)) && lane == 0) {
             // ===================== TMA producers =====================
             // Two issuing threads share the work of a stage (16 box loads of 4 KB): warp 0 arms the barrier and loads the
             // S tile + the first Bg tap, warp 3 loads the remaining taps.  Both wait on the same empty barrier.
@@ -115,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                 mbar_wait(&empty_bar[stage], ph ^ 1);
                 uint8_t* a_dst = smem + stage * L::kStageBytes;
                 uint8_t* b_dst = a_dst + L::kABytes;
-                if (first) mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                if (first) mbar_expect_tx(&full_bar[stage], L::kTxBytes);
                 for (int r = 0; r < rows; ++r) {
                     long long grow;                          // global row index n*Hs + y
                     int x0;
@@ -131,6 +144,12 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                                 tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
                         }
                     }
+                    if (HALO) {      // one (32+2)-pixel tile per 32-channel chunk, starting one pixel to the left
+                        for (int c = 0; c < L::kBChunks; ++c)
+                            tma_load_4d(b_dst + c * kHaloChunkBytes, &map_b, &full_bar[stage], nb * BLOCK_N + c * 32, x0 - 1,
+                                        y + (STACK ? 0 : kh - p.pad), n);
+                        continue;
+                    }
                     for (int kw = first ? 0 : 1; kw < (first ? 1 : KW); ++kw)
                         for (int c = 0; c < L::kBChunks; ++c) {
                             uint8_t* dst = b_dst + kw * L::kBBytesPerTap + c * kChunkBytes + r * row_bytes;
@@ -143,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                                 tma_load_5d(dst, &map_b, &full_bar[stage], ch, kw & 1, x0 + (kw >> 1), 2 * y + kh, n);
                         }
                 }
-                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+                if (++stage == kNStages) { stage = 0; ph ^= 1; }
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
@@ -158,13 +177,15 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                 const uint64_t adesc = make_mnmajor_sw128b32_desc(a_addr, kChunkBytes);
 #pragma unroll
                 for (int kw = 0; kw < KW; ++kw) {
-                    const uint64_t bdesc = make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
+                    const uint64_t bdesc = HALO
+                        ? make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * 128, kHaloChunkBytes, p.halo_bo ? kw : 0)
+                        : make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
 #pragma unroll
                     for (int j = 0; j < kPix / 8; ++j)   // 8 pixels per MMA: next swizzle atom = +1024 B (>>4 = 64)
                         umma_tf32(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
                 }
                 umma_commit(&empty_bar[stage]);
-                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+                if (++stage == kNStages) { stage = 0; ph ^= 1; }
             }
             umma_commit(tmem_full_bar);
         } else if (warp >= 4) {
@@ -243,17 +264,17 @@ int pick_bn(int Cb) {
     return 0;
 }
 
-template <int KW, int BLOCK_N, bool STACK>
+template <int KW, int BLOCK_N, bool STACK, bool HALO>
 int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, float* part, const WgParams& p, cudaStream_t st) {
-    using L = WgSmem<KW, BLOCK_N>;
+    using L = WgSmem<KW, BLOCK_N, HALO>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(wgrad_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
     dim3 grid(STACK ? 1 : p.Cs / 128, p.Cb / BLOCK_N, STACK ? p.splits : p.k * p.splits);
-    wgrad_tc_kernel<KW, BLOCK_N, STACK><<<grid, 256, L::kDynamic, st>>>(ms, mb, part, p);
+    wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO><<<grid, 256, L::kDynamic, st>>>(ms, mb, part, p);
     GIFB200_LAUNCH_CHECK("wgrad_tc_kernel");
     const int T = p.k * p.k;
     const long long total = static_cast<long long>(T) * p.Cs * p.Cb;
@@ -342,11 +363,17 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         int rc = encode_map(&ms, S, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     }
+    // GIFB200_WGRAD_HALO: 0 = off, 1 = on (default).  Measured on B200: a tile start address that is a whole number of
+    // 128-byte rows into a swizzle atom needs base_offset = 0 (the swizzle is a function of the absolute shared-memory
+    // address bits); setting base_offset to the row phase (value 2 here) gives wrong results.
+    static const int halo_env = [] { const char* e = getenv("GIFB200_WGRAD_HALO"); return e ? atoi(e) : 1; }();
+    const bool halo = halo_env > 0 && mode == 0 && k == 3 && p.pw == kPix;
+    p.halo_bo = halo_env == 2;
     if (!p.s2) {
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cb), static_cast<cuuint64_t>(p.Wb), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Wb) * p.Cb * 4,
                                        static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
-        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
+        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(halo ? kHaloRows : p.pw), 1, 1};
         int rc = encode_map(&mb, Bg, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     } else {
@@ -357,10 +384,16 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         int rc = encode_map(&mb, Bg, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (rc != GIFB200_OK) return rc;
     }
-#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false>(ms, mb, gw, part, p, st)
+#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false, false>(ms, mb, gw, part, p, st)
+    if (stack && halo)
+        return bn == 128 ? launch_wg<3, 128, true, true>(ms, mb, gw, part, p, st)
+               : bn == 64 ? launch_wg<3, 64, true, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true, true>(ms, mb, gw, part, p, st);
     if (stack)
-        return bn == 128 ? launch_wg<3, 128, true>(ms, mb, gw, part, p, st)
-               : bn == 64 ? launch_wg<3, 64, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true>(ms, mb, gw, part, p, st);
+        return bn == 128 ? launch_wg<3, 128, true, false>(ms, mb, gw, part, p, st)
+               : bn == 64 ? launch_wg<3, 64, true, false>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true, false>(ms, mb, gw, part, p, st);
+    if (halo)
+        return bn == 128 ? launch_wg<3, 128, false, true>(ms, mb, gw, part, p, st)
+               : bn == 64 ? launch_wg<3, 64, false, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, false, true>(ms, mb, gw, part, p, st);
     if (k == 3) return bn == 128 ? GIFB200_WG(3, 128) : bn == 64 ? GIFB200_WG(3, 64) : GIFB200_WG(3, 32);
     return bn == 128 ? GIFB200_WG(1, 128) : bn == 64 ? GIFB200_WG(1, 64) : GIFB200_WG(1, 32);
 #undef GIFB200_WG
