@@ -133,6 +133,81 @@ __global__ void __launch_bounds__(256) spatial_dot_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------ fused backward passes
+// Backward of the StyledConv tail y = lrelu(acc*d[b,c] + noise + bias[c])*gain in ONE pass over (gy, y, acc):
+//   gt = gy*gain*(y>0 ? 1 : slope)   (gradient of the pre-activation: goes to the noise branch)      -> written
+//   gacc = gt*d[b,c]                 (gradient of the convolution accumulator)                       -> written
+//   gb[c] += sum gt ;  gd[b,c] += sum gt*acc                                                          -> reduced
+// instead of four kernels (act_bwd, chan_scale, spatial_dot, rows_sum) that read gt three more times.
+__global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                       const float* __restrict__ acc, const float* __restrict__ d,
+                                                       float* __restrict__ gt, float* __restrict__ gacc,
+                                                       float* __restrict__ gb, float* __restrict__ gd, int rows, int C,
+                                                       int rows_per_block, float slope, float gain, int rtf32) {
+    __shared__ float sm[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float sb = 0.f, sd = 0.f;
+    if (c < C) {
+        const float dv = d ? d[static_cast<long long>(b) * C + c] : 1.f;
+        const long long base = (static_cast<long long>(b) * rows) * C + c;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const long long i = base + static_cast<long long>(r) * C;
+            float g = __ldcs(gy + i) * gain * (__ldcs(y + i) > 0.f ? 1.f : slope);
+            float ga = g * dv;
+            sb += g;
+            if (gd) sd += g * __ldcs(acc + i);
+            if (rtf32) { g = round_tf32(g); ga = round_tf32(ga); }
+            gt[i] = g;
+            if (gacc) gacc[i] = ga;
+        }
+    }
+    sm[0][threadIdx.y][threadIdx.x] = sb;
+    sm[1][threadIdx.y][threadIdx.x] = sd;
+    __syncthreads();
+    if (threadIdx.y < 2 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[threadIdx.y][j][threadIdx.x];
+        if (threadIdx.y == 0) { if (gb) atomicAdd(gb + c, t); }
+        else if (gd) atomicAdd(gd + static_cast<long long>(b) * C + c, t);
+    }
+}
+
+// Backward of y = x*s[b,c] in one pass over (gy, x):  gx = gy*s (written),  gs[b,c] += sum gy*x (reduced).
+__global__ void __launch_bounds__(256) scale_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                        const float* __restrict__ s, float* __restrict__ gx,
+                                                        float* __restrict__ gs, int rows, int C, int rows_per_block,
+                                                        int rtf32) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.f;
+    if (c < C) {
+        const float sv = s[static_cast<long long>(b) * C + c];
+        const long long base = (static_cast<long long>(b) * rows) * C + c;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const long long i = base + static_cast<long long>(r) * C;
+            const float g = __ldcs(gy + i);
+            acc += g * __ldcs(x + i);
+            const float o = g * sv;
+            gx[i] = rtf32 ? round_tf32(o) : o;
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        atomicAdd(gs + static_cast<long long>(b) * C + c, t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ chan_scale
 template <bool VEC>
 __global__ void __launch_bounds__(256) chan_scale_kernel(const float* __restrict__ x, const float* __restrict__ s,
@@ -408,6 +483,46 @@ int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int 
     GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "spatial_dot: grid too large");
     spatial_dot_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(a, b2, out, P, C, rpb);
     GIFB200_LAUNCH_CHECK("spatial_dot_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
+                     float* gb, float* gd, int B, int P, int C, float slope, float gain, int rtf32, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "tail_bwd: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) return GIFB200_OK;
+    if (gb) {
+        cudaError_t e = cudaMemsetAsync(gb, 0, sizeof(float) * C, st);
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "tail_bwd memset", cudaGetErrorString(e));
+    }
+    if (gd) {
+        cudaError_t e = cudaMemsetAsync(gd, 0, sizeof(float) * static_cast<size_t>(B) * C, st);
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "tail_bwd memset", cudaGetErrorString(e));
+    }
+    if (P == 0) return GIFB200_OK;
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(P, cb, B, &rpb);
+    GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "tail_bwd: grid too large");
+    tail_bwd_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
+    GIFB200_LAUNCH_CHECK("tail_bwd_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx, float* gs, int B, int P, int C, int rtf32,
+                      gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "scale_bwd: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) return GIFB200_OK;
+    cudaError_t e = cudaMemsetAsync(gs, 0, sizeof(float) * static_cast<size_t>(B) * C, st);
+    if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "scale_bwd memset", cudaGetErrorString(e));
+    if (P == 0) return GIFB200_OK;
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(P, cb, B, &rpb);
+    GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "scale_bwd: grid too large");
+    scale_bwd_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gy, x, s, gx, gs, P, C, rpb, rtf32);
+    GIFB200_LAUNCH_CHECK("scale_bwd_kernel");
     return GIFB200_OK;
 }
 

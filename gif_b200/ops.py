@@ -308,6 +308,26 @@ class _BiasAct(torch.autograd.Function):
     def backward(ctx, gy):
         x, rowscale, y = ctx.saved_tensors
         slope, gain, bias_shape, has_add = ctx.cfg
+        if not torch.is_grad_enabled():
+            # first-order backward only (no create_graph): one fused pass instead of act_bwd + chan_scale + spatial_dot + rows_sum
+            gy = _c(gy)
+            rt = tf32_enabled()
+            B, C = gy.shape[0], gy.shape[-1]
+            P = gy.numel() // max(B * C, 1)
+            gt = torch.empty_like(gy)
+            gacc = torch.empty_like(gy) if rowscale is not None else None
+            want_b = bias_shape is not None and ctx.needs_input_grad[3]
+            want_d = rowscale is not None and ctx.needs_input_grad[1]
+            gb = torch.empty(C, dtype=torch.float32, device=gy.device) if want_b else None
+            gd = torch.empty((B, C), dtype=torch.float32, device=gy.device) if want_d else None
+            check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(x), ptr(rowscale), ptr(gt), ptr(gacc), ptr(gb), ptr(gd), B, P, C,
+                                       slope, gain, int(rt), stream()), "gifb200_tail_bwd")
+            _tag(gt, rt)
+            if gacc is not None:
+                _tag(gacc, rt)
+            gx = (gacc if rowscale is not None else gt) if ctx.needs_input_grad[0] else None
+            return (gx, gd, gt if (has_add and ctx.needs_input_grad[2]) else None,
+                    gb.reshape(bias_shape) if want_b else None, None, None, None)
         gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())   # gradient w.r.t. the pre-activation t (feeds dgrad/wgrad)
         gx = grs = gadd = gb = None
         if ctx.needs_input_grad[0]:
@@ -391,6 +411,16 @@ class _ChanScale(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, s = ctx.saved_tensors
+        if not torch.is_grad_enabled() and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            gy = _c(gy)                                    # fused first-order pass: gx = gy*s, gs = sum gy*x
+            rt = tf32_enabled()
+            B, C = gy.shape[0], gy.shape[-1]
+            P = gy.numel() // max(B * C, 1)
+            gx = torch.empty_like(gy)
+            gs = torch.empty((B, C), dtype=torch.float32, device=gy.device)
+            check(lib.gifb200_scale_bwd(ptr(gy), ptr(x), ptr(s), ptr(gx), ptr(gs), B, P, C, int(rt), stream()),
+                  "gifb200_scale_bwd")
+            return _tag(gx, rt), gs, None
         gx = chan_scale(gy, s, tf32_enabled()) if ctx.needs_input_grad[0] else None
         gs = spatial_dot(gy, x) if ctx.needs_input_grad[1] else None
         return gx, gs, None

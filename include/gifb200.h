@@ -117,6 +117,15 @@ int gifb200_rows_sum(const float* x, float* out, int G, int rows, int C, gifb200
  * the tcgen05 kind::tf32 contraction, which truncates, sees exactly representable operands. */
 int gifb200_chan_scale(const float* x, const float* s, float* y, int B, int P, int C, int round_tf32,
                        gifb200_stream_t stream);
+/* Fused first-order backward passes (used when no second derivative is requested; the composable primitives above remain
+ * the definition).  tail_bwd: backward of t = acc*d[b,c] + add + bias[c], y = lrelu(t)*gain given (gy, y, acc):
+ *   gt = gy*gain*(y>0?1:slope) (= grad of add, of the noise branch), gacc = gt*d (may be NULL), gb[c] = sum gt (may be
+ *   NULL), gd[b,c] = sum_p gt*acc (may be NULL; d == NULL means d = 1).  Replaces act_bwd + chan_scale + spatial_dot +
+ *   rows_sum (autograd of cl.py:479-486).  scale_bwd: backward of y = x*s[b,c]: gx = gy*s, gs[b,c] = sum_p gy*x. */
+int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc, float* gb,
+                     float* gd, int B, int P, int C, float slope, float gain, int round_tf32, gifb200_stream_t stream);
+int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx, float* gs, int B, int P, int C,
+                      int round_tf32, gifb200_stream_t stream);
 /* out[b,c] = sum_p a[b,p,c] * b2[b,p,c]  (gradient of chan_scale w.r.t. s). out is OVERWRITTEN. */
 int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream);
 /* y = alpha*a + beta*b (b may be NULL): residual merge (a+b)/sqrt2 of ResBlock.forward (cl.py:817-818),
