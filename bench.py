@@ -271,7 +271,12 @@ def main():
     trainer.replayed_launches = 0
     use_graph = trainer._graphs is not None
     ops.PROFILE = [] if (rank == 0 and not use_graph) else None
+    cuprof = bool(os.environ.get("GIFB200_CUPROFILE"))   # `ncu --profile-from-start off`: capture exactly the timed steps
+    if cuprof:
+        torch.cuda.profiler.start()
     ms = timed(args.steps, False)
+    if cuprof:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0 + trainer.replayed_launches
     prof = ops.PROFILE
     ops.PROFILE = None

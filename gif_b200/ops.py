@@ -216,14 +216,30 @@ class _ConvBiasAct(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         k, mode, slope, gain, in_hw, x_tf32, bias_shape = ctx.cfg
         _tag(x, x_tf32)
-        gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())
-        gx = gw = gb = None
+        gb = None
+        if not torch.is_grad_enabled():
+            # first-order backward: activation backward and bias gradient in one pass over (gy, y)
+            gy = _c(gy)
+            rt = tf32_enabled()
+            C = gy.shape[-1]
+            rows = gy.numel() // max(C, 1)
+            gt = torch.empty_like(gy)
+            want_b = bias_shape is not None and ctx.needs_input_grad[2]
+            gbf = torch.empty(C, dtype=torch.float32, device=gy.device) if want_b else None
+            check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(y), None, ptr(gt), None, ptr(gbf), None, 1, rows, C, slope, gain,
+                                       int(rt), stream()), "gifb200_tail_bwd")
+            _tag(gt, rt)
+            if want_b:
+                gb = gbf.reshape(bias_shape)
+        else:
+            gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())
+            if bias_shape is not None and ctx.needs_input_grad[2]:
+                gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
+        gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = _Conv.apply(gt, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
         if ctx.needs_input_grad[1]:
             gw = _ConvWgrad.apply(x, gt, k, mode, False, False)
-        if bias_shape is not None and ctx.needs_input_grad[2]:
-            gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
         return gx, gw, gb, None, None, None, None, None, None
 
 
