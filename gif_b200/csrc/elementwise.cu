@@ -208,6 +208,100 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(const float* __restrict_
     }
 }
 
+
+// 16-byte-per-lane variants of the two kernels above for C % 32 == 0 (every layer of the model): a thread owns 4
+// channels, TX lanes span TX*4 channels of one pixel row, 256/TX rows per block step; the row loop is unrolled so
+// that 8-12 independent 16-byte loads are in flight per thread (the scalar kernels reach ~2.7 TB/s, these ~HBM rate).
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float4 f4_round(float4 v) {
+    return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+__device__ __forceinline__ void f4_atomic_add(float* p, const float4& v) {
+    atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+}
+
+template <int TX>
+__global__ void __launch_bounds__(256) tail_bwd_vec_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                           const float* __restrict__ acc, const float* __restrict__ d,
+                                                           float* __restrict__ gt, float* __restrict__ gacc,
+                                                           float* __restrict__ gb, float* __restrict__ gd, int rows, int C,
+                                                           int rows_per_block, float slope, float gain, int rtf32) {
+    constexpr int TY = 256 / TX;
+    __shared__ float4 sm[2][TY][TX];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = (blockIdx.x * TX + tx) * 4;          // first of this thread's 4 channels (C % (4*TX) == 0)
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float4 sb = f4_zero(), sd = f4_zero();
+    const float4 dv = d ? *reinterpret_cast<const float4*>(d + static_cast<long long>(b) * C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const long long base = (static_cast<long long>(b) * rows) * C + c;
+    const bool has_acc = gd != nullptr;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += TY) {
+        const long long i = base + static_cast<long long>(r) * C;
+        const float4 g0 = __ldcs(reinterpret_cast<const float4*>(gy + i));
+        const float4 yv = __ldcs(reinterpret_cast<const float4*>(y + i));
+        float4 g = make_float4(g0.x * gain * (yv.x > 0.f ? 1.f : slope), g0.y * gain * (yv.y > 0.f ? 1.f : slope),
+                               g0.z * gain * (yv.z > 0.f ? 1.f : slope), g0.w * gain * (yv.w > 0.f ? 1.f : slope));
+        f4_add(sb, g);
+        if (has_acc) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(acc + i));
+            sd.x += g.x * a.x; sd.y += g.y * a.y; sd.z += g.z * a.z; sd.w += g.w * a.w;
+        }
+        float4 ga = make_float4(g.x * dv.x, g.y * dv.y, g.z * dv.z, g.w * dv.w);
+        if (rtf32) { g = f4_round(g); ga = f4_round(ga); }
+        *reinterpret_cast<float4*>(gt + i) = g;
+        if (gacc) *reinterpret_cast<float4*>(gacc + i) = ga;
+    }
+    sm[0][ty][tx] = sb;
+    sm[1][ty][tx] = sd;
+    __syncthreads();
+    if (ty < 2) {
+        float4 t = f4_zero();
+#pragma unroll
+        for (int j = 0; j < TY; ++j) f4_add(t, sm[ty][j][tx]);
+        if (ty == 0) { if (gb) f4_atomic_add(gb + c, t); }
+        else if (gd) f4_atomic_add(gd + static_cast<long long>(b) * C + c, t);
+    }
+}
+
+template <int TX>
+__global__ void __launch_bounds__(256) scale_bwd_vec_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                            const float* __restrict__ s, float* __restrict__ gx,
+                                                            float* __restrict__ gs, int rows, int C, int rows_per_block,
+                                                            int rtf32) {
+    constexpr int TY = 256 / TX;
+    __shared__ float4 sm[TY][TX];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = (blockIdx.x * TX + tx) * 4;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float4 a = f4_zero();
+    const float4 sv = *reinterpret_cast<const float4*>(s + static_cast<long long>(b) * C + c);
+    const long long base = (static_cast<long long>(b) * rows) * C + c;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += TY) {
+        const long long i = base + static_cast<long long>(r) * C;
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(gy + i));
+        const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + i));
+        a.x += g.x * xv.x; a.y += g.y * xv.y; a.z += g.z * xv.z; a.w += g.w * xv.w;
+        float4 o = make_float4(g.x * sv.x, g.y * sv.y, g.z * sv.z, g.w * sv.w);
+        if (rtf32) o = f4_round(o);
+        *reinterpret_cast<float4*>(gx + i) = o;
+    }
+    sm[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0) {
+        float4 t = f4_zero();
+#pragma unroll
+        for (int j = 0; j < TY; ++j) f4_add(t, sm[j][tx]);
+        f4_atomic_add(gs + static_cast<long long>(b) * C + c, t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ chan_scale
 template <bool VEC>
 __global__ void __launch_bounds__(256) chan_scale_kernel(const float* __restrict__ x, const float* __restrict__ s,
@@ -454,6 +548,20 @@ static int rows_split(int rows, int cblocks, int G, int* rows_per_block) {
     return (rows + rpb - 1) / rpb;
 }
 
+// lanes along the channel dimension for the 16-byte kernels: the largest of 32/16/8 such that C % (4*lanes) == 0
+static int vec_lanes(int C) { return (C % 128 == 0) ? 32 : (C % 64 == 0) ? 16 : 8; }
+
+static int rows_split_vec(int rows, int cblocks, int G, int ty, int* rows_per_block) {
+    // ~8 blocks of 256 threads per SM in total; at least 4 unrolled row steps per block
+    long long want = (static_cast<long long>(kNumSMs) * 8 + static_cast<long long>(cblocks) * G - 1) /
+                     (static_cast<long long>(cblocks) * G);
+    if (want < 1) want = 1;
+    int rpb = static_cast<int>((rows + want - 1) / want);
+    if (rpb < 4 * ty) rpb = 4 * ty;
+    *rows_per_block = rpb;
+    return (rows + rpb - 1) / rpb;
+}
+
 int gifb200_rows_sum(const float* x, float* out, int G, int rows, int C, gifb200_stream_t stream) {
     GIFB200_REQUIRE(G >= 0 && rows >= 0 && C > 0, GIFB200_E_SHAPE, "rows_sum: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -500,6 +608,20 @@ int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const fl
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "tail_bwd memset", cudaGetErrorString(e));
     }
     if (P == 0) return GIFB200_OK;
+    if (C % 32 == 0 && aligned16(gy) && aligned16(y) && aligned16(gt) && (!gd || aligned16(acc)) && (!gacc || aligned16(gacc)) &&
+        (!d || aligned16(d))) {
+        const int tx = vec_lanes(C);
+        int rpb;
+        const int cbv = C / (4 * tx);
+        const int rb = rows_split_vec(P, cbv, B, 256 / tx, &rpb);
+        GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "tail_bwd: grid too large");
+        const dim3 grid(cbv, rb, B);
+        if (tx == 32) tail_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
+        else if (tx == 16) tail_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
+        else tail_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
+        GIFB200_LAUNCH_CHECK("tail_bwd_vec_kernel");
+        return GIFB200_OK;
+    }
     const int cb = cdiv(C, 32);
     int rpb;
     const int rb = rows_split(P, cb, B, &rpb);
@@ -517,6 +639,19 @@ int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx
     cudaError_t e = cudaMemsetAsync(gs, 0, sizeof(float) * static_cast<size_t>(B) * C, st);
     if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "scale_bwd memset", cudaGetErrorString(e));
     if (P == 0) return GIFB200_OK;
+    if (C % 32 == 0 && aligned16(gy) && aligned16(x) && aligned16(gx) && aligned16(s)) {
+        const int tx = vec_lanes(C);
+        int rpb;
+        const int cbv = C / (4 * tx);
+        const int rb = rows_split_vec(P, cbv, B, 256 / tx, &rpb);
+        GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "scale_bwd: grid too large");
+        const dim3 grid(cbv, rb, B);
+        if (tx == 32) scale_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(gy, x, s, gx, gs, P, C, rpb, rtf32);
+        else if (tx == 16) scale_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(gy, x, s, gx, gs, P, C, rpb, rtf32);
+        else scale_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(gy, x, s, gx, gs, P, C, rpb, rtf32);
+        GIFB200_LAUNCH_CHECK("scale_bwd_vec_kernel");
+        return GIFB200_OK;
+    }
     const int cb = cdiv(C, 32);
     int rpb;
     const int rb = rows_split(P, cb, B, &rpb);

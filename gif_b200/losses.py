@@ -57,9 +57,15 @@ class PathLengthRegularizor:
         pl_lengths = torch.mean(torch.sqrt(torch.sum(torch.pow(pl_grads, 2), dim=1)))   # losses.py:116
         # losses.py:119 as written (no stop-gradient: the new mean == decay * length and carries its gradient into the
         # penalty); only the value kept for the next call is detached so that no graph outlives the iteration.
+        # The running mean lives in ONE persistent 0-d device tensor updated in place: a captured CUDA graph reads and
+        # writes it at a fixed address (rebinding the attribute to a fresh tensor every call would leave a replayed
+        # graph reading the freed tensor of capture time).
+        if not torch.is_tensor(self.pl_moving_mean):
+            self.pl_moving_mean = torch.full((), float(self.pl_moving_mean), dtype=pl_lengths.dtype, device=pl_lengths.device)
         ema = self.pl_moving_mean + self.pl_decay * pl_lengths - self.pl_moving_mean
-        self.pl_moving_mean = ema.detach()
-        return torch.pow(pl_lengths - ema, 2)                                    # losses.py:122
+        penalty = torch.pow(pl_lengths - ema, 2)                                 # losses.py:122
+        self.pl_moving_mean.copy_(ema.detach())
+        return penalty
 
 
 def _synth_from_w(g, w, cond, step):

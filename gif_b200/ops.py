@@ -62,15 +62,19 @@ def _round_tf32_raw(x):
 PROFILE = None   # bench.py sets this to a list; every tensor-core conv launch then appends (ev0, ev1, flops, tag)
 
 _ws_cache = {}
+_ws_retired = []
 
 
 def _workspace(nbytes, device):
-    """A per-device scratch buffer, grown on demand (stream-ordered reuse: all our launches are on the current stream)."""
+    """A per-(device, stream) scratch buffer, grown on demand (stream-ordered reuse: all our launches are on the current
+    stream).  A superseded buffer is retired, never freed: a captured CUDA graph may hold its address."""
     if nbytes == 0:
         return None
     key = (device.index, torch.cuda.current_stream().cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf

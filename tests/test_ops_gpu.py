@@ -78,6 +78,29 @@ def test_upfirdn2d_backward_and_double_backward(cuda, fp32_mode, c, up, down, pa
     close(nchw(gg), O.upfirdn2d(v, k, up, down, pad), TOL32, "double bwd")
 
 
+@pytest.mark.parametrize("c,h,w", [(32, 21, 19), (64, 16, 40), (32, 9, 8)])
+@pytest.mark.parametrize("pad", [(1, 1), (0, 0), (2, 2), (2, 1)])
+def test_upfirdn2d_down2_tiled_kernel(cuda, fp32_mode, c, h, w, pad):
+    """the shared-memory tiled decimating FIR (C % 32 == 0, 4x4, down 2): ragged tile edges, every pad the model uses,
+    asymmetric kernel; forward vs the oracle and, through the up=2 call whose adjoint it is, the flipped variant."""
+    from gif_b200 import ops
+    k = gu.randn((4, 4), 15)
+    x = gu.randn((2, c, h, w), 16)
+    y = ops.upfirdn2d(nhwc(x, cuda), k.to(cuda), 1, 2, pad)
+    close(nchw(y), O.upfirdn2d(x, k, 1, 2, pad), TOL32, "down2 fwd")
+    # adjoint of up=2 (runs the same kernel with flip=1 and pad' = k-1-pad)
+    xs = gu.randn((2, c, h // 2 + 1, w // 2 + 1), 17)
+    xg = nhwc(xs, cuda).requires_grad_(True)
+    yu = ops.upfirdn2d(xg, k.to(cuda), 2, 1, pad)
+    xo = xs.clone().requires_grad_(True)
+    yo = O.upfirdn2d(xo, k, 2, 1, pad)
+    close(nchw(yu), yo, TOL32, "up2 fwd")
+    gy = gu.randn(tuple(yo.shape), 18)
+    (gx,) = torch.autograd.grad(yu, xg, nhwc(gy, cuda))
+    (gxo,) = torch.autograd.grad(yo, xo, gy)
+    close(nchw(gx), gxo, TOL32, "up2 bwd (down2 kernel, flipped)")
+
+
 # ------------------------------------------------------------------------------------------------ small ops
 def test_small_ops_golden(cuda):
     from gif_b200.model import stylegan2_common_layers as cl
@@ -222,3 +245,31 @@ def test_sgemm_shapes_incl_split_k(cuda, m, n, k, ta, tb):
     gao, gbo = torch.autograd.grad(co, [ao, bo], g.double())
     close(ga, gao, 2e-5, "dA")
     close(gb, gbo, 2e-5, "dB")
+
+
+# ------------------------------------------------------------------------------------------------ fused first-order backwards
+@pytest.mark.parametrize("c", [32, 64, 128, 96, 20])
+def test_fused_tail_and_scale_backward(cuda, fp32_mode, c):
+    """first-order backward (no create_graph) of the StyledConv tail and of the input modulation: the single-pass
+    kernels (16-byte variants for C % 32 == 0 with 8/16/32 channel lanes, scalar otherwise) against torch autograd on the
+    same formulas, and against this package's own closed-set (create_graph=True) path."""
+    from gif_b200 import ops
+    b, h, w = 3, 13, 11
+    acc = gu.randn((b, h, w, c), 31).to(cuda)
+    d = (gu.rand_uniform((b, c), 32) + 1.5).to(cuda)
+    noise = gu.randn((b, h, w, c), 33).to(cuda)
+    bias = gu.randn((c,), 34).to(cuda)
+    gy = gu.randn((b, h, w, c), 35).to(cuda)
+    s = gu.randn((b, c), 36).to(cuda)
+
+    def ours(create_graph):
+        a, dd, nn, bb, ss = (t.clone().requires_grad_(True) for t in (acc, d, noise, bias, s))
+        y = ops.bias_act(ops.chan_scale(a, ss), bb, 0.2, math.sqrt(2.0), rowscale=dd, add=nn)
+        return torch.autograd.grad(y, (a, dd, nn, bb, ss), gy, create_graph=create_graph)
+
+    a, dd, nn, bb, ss = (t.clone().requires_grad_(True) for t in (acc, d, noise, bias, s))
+    pre = (a * ss[:, None, None, :]) * dd[:, None, None, :] + nn + bb
+    ref = torch.autograd.grad(torch.nn.functional.leaky_relu(pre, 0.2) * math.sqrt(2.0), (a, dd, nn, bb, ss), gy)
+    for name, g1, g2, r in zip(("acc", "demod", "noise", "bias", "style"), ours(False), ours(True), ref):
+        close(g1, r, TOL32, f"fused first-order grad[{name}]")
+        close(g2, r, TOL32, f"closed-set grad[{name}]")
