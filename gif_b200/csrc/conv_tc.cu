@@ -107,8 +107,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===================== TMA producer =====================
+        // Lane 0 owns the barriers.  In stride-2 mode the A tile is nt*ht separate row boxes (the parity view cannot be
+        // one box): the 32 lanes issue them in parallel -- at 9x9 / 17x17 inputs a stage is 32 / 16 row loads and a
+        // single issuing thread was the whole critical path (340 us for a 2.4 GFLOP layer).
         int stage = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -123,22 +126,27 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
             const int iters = p.phase_ntaps[phase] * kchunks;
             for (int it = 0; it < iters; ++it) {
                 const int tap = it / kchunks, c0 = (it % kchunks) * kBlockK;
-                mbar_wait(&empty_bar[stage], ph ^ 1);
                 uint8_t* a_dst = smem + stage * L::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
-                mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[stage], ph ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                }
+                __syncwarp();
                 const int dy = p.tap_dy[phase][tap], dx = p.tap_dx[phase][tap];
                 if (!p.s2) {
-                    tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+                    if (lane == 0) tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
                 } else {
                     const int par = p.tap_par[phase][tap];
                     const int row_bytes = p.wt * kBlockK * 4;
-                    for (int n = 0; n < p.nt; ++n)
-                        for (int h = 0; h < p.ht; ++h)
-                            tma_load_5d(a_dst + (n * p.ht + h) * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
-                                        (y0 + h) * p.in_sy + dy, n0 + n);
+                    const int rows = p.nt * p.ht;
+                    for (int r = lane; r < rows; r += 32) {
+                        const int n = r / p.ht, h = r - n * p.ht;
+                        tma_load_5d(a_dst + r * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
+                                    (y0 + h) * p.in_sy + dy, n0 + n);
+                    }
                 }
-                tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+                if (lane == 0) tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
                 if (++stage == kStages) { stage = 0; ph ^= 1; }
             }
         }

@@ -283,6 +283,18 @@ __global__ void __launch_bounds__(256, 2) upfirdn2d_fir4_pipe_kernel(const float
     float kreg[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) kreg[i] = p.flip ? __ldg(kernel + 15 - i) : __ldg(kernel + i);
+    // rank-1 kernel (every Blur of the model: outer([1,3,3,1]) * gain / 64)?  Exact test, uniform across the grid.
+    bool separable = DOWN == 1 && kreg[0] != 0.f;
+    float kcol[4], krow[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        kcol[a] = kreg[a * 4];
+        krow[a] = separable ? kreg[a] / kreg[0] : 0.f;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) separable = separable && (kcol[a] * krow[b] == kreg[a * 4 + b]);
     const int cchunks = p.C >> 5;
 
     auto decode = [&](int t, int& b, int& y0, int& x0, int& cc) {
@@ -291,19 +303,28 @@ __global__ void __launch_bounds__(256, 2) upfirdn2d_fir4_pipe_kernel(const float
         y0 = (t % tiles_y) * TO;
         b = t / tiles_y;
     };
+    // per-thread tile coordinates of its first element; the k-th element is 32 pixels further (256 threads / 8 lanes)
+    const int c4l = threadIdx.x & 7;
+    const int pix0 = threadIdx.x >> 3;
+    const int py_first = pix0 / TI, px_first = pix0 - py_first * TI;
     auto issue = [&](int t, int buf) {
         int b, y0, x0, cc;
         decode(t, b, y0, x0, cc);
         const int ix0 = DOWN * x0 - p.px0, iy0 = DOWN * y0 - p.py0;
-        const float* xb = x + static_cast<long long>(b) * p.Hi * p.Wi * p.C + cc * 32;
-        float4* dst = fir_smem + buf * TILE_F4;
-        for (int idx = threadIdx.x; idx < TILE_F4; idx += 256) {
-            const int c4 = idx & 7, pix = idx >> 3;
-            const int px = pix % TI, py = pix / TI;
-            const int gx = ix0 + px, gy = iy0 + py;
-            const bool ok = gx >= 0 && gx < p.Wi && gy >= 0 && gy < p.Hi;
-            const float* src = ok ? xb + (static_cast<long long>(gy) * p.Wi + gx) * p.C + c4 * 4 : x;
-            cp_async16(dst + idx, src, ok ? 16 : 0);
+        const float* xb = x + static_cast<long long>(b) * p.Hi * p.Wi * p.C + cc * 32 + c4l * 4;
+        float4* dst = fir_smem + buf * TILE_F4 + threadIdx.x;
+        int px = px_first, py = py_first;
+#pragma unroll
+        for (int k = 0; k < (TILE_F4 + 255) / 256; ++k) {
+            if (k * 256 + static_cast<int>(threadIdx.x) < TILE_F4) {
+                const int gx = ix0 + px, gy = iy0 + py;
+                const bool ok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.Wi) &&
+                                static_cast<unsigned>(gy) < static_cast<unsigned>(p.Hi);
+                const float* src = ok ? xb + (static_cast<long long>(gy) * p.Wi + gx) * p.C : x;
+                cp_async16(dst + k * 256, src, ok ? 16 : 0);
+            }
+            px += 32 - TI; py += 1;                       // +32 pixels, TI < 32 < 2*TI
+            if (px >= TI) { px -= TI; py += 1; }
         }
         cp_async_commit();
     };
@@ -324,18 +345,39 @@ __global__ void __launch_bounds__(256, 2) upfirdn2d_fir4_pipe_kernel(const float
             float4 acc[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (separable) {
+                // K[a][b] = kcol[a] * krow[b]: one horizontal 4-tap pass per input row, then the vertical taps
+                // (11*16 + 32*4 = 304 FMAs per thread instead of 512)
 #pragma unroll
-            for (int j = 0; j < R + 3; ++j) {
-                const int row = half * R + j;
+                for (int j = 0; j < R + 3; ++j) {
+                    const int row = half * R + j;
+                    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) {
-                    const float4 v = tile[(row * TI + lx + 3 - bb) * 8 + c4];
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const float4 v = tile[(row * TI + lx + 3 - bb) * 8 + c4];
+                        h.x += krow[bb] * v.x; h.y += krow[bb] * v.y; h.z += krow[bb] * v.z; h.w += krow[bb] * v.w;
+                    }
 #pragma unroll
                     for (int i = 0; i < R; ++i) {
                         const int a = 3 - (j - i);
                         if (a < 0 || a > 3) continue;
-                        const float kv = kreg[a * 4 + bb];
-                        acc[i].x += kv * v.x; acc[i].y += kv * v.y; acc[i].z += kv * v.z; acc[i].w += kv * v.w;
+                        acc[i].x += kcol[a] * h.x; acc[i].y += kcol[a] * h.y; acc[i].z += kcol[a] * h.z; acc[i].w += kcol[a] * h.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < R + 3; ++j) {
+                    const int row = half * R + j;
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) {
+                        const float4 v = tile[(row * TI + lx + 3 - bb) * 8 + c4];
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            const int a = 3 - (j - i);
+                            if (a < 0 || a > 3) continue;
+                            const float kv = kreg[a * 4 + bb];
+                            acc[i].x += kv * v.x; acc[i].y += kv * v.y; acc[i].z += kv * v.z; acc[i].w += kv * v.w;
+                        }
                     }
                 }
             }
@@ -387,6 +429,109 @@ __global__ void __launch_bounds__(256, 2) upfirdn2d_fir4_pipe_kernel(const float
     }
 }
 
+// Zero-insert x2 upsampling + 4x4 FIR (the adjoint of every decimating call: D's skip / blur backward) for C % 32 == 0,
+// same persistent cp.async double-buffered scheme.  An output pixel sees only the 2 x 2 taps whose zero-inserted
+// position is even, so a 16 x 16 output tile needs a 10 x 10 input tile (12.5 KB); which taps apply depends on the
+// output row / column parity: the 16 kernel values are permuted once per thread into kk[row parity][s][t] (the column
+// parity is fixed per thread), everything else is compile-time indexed.
+constexpr int kUT = 16;                 // output tile edge
+constexpr int kUTI = kUT / 2 + 2;       // input tile edge
+__global__ void __launch_bounds__(256, 4) upfirdn2d_up2_pipe_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ kernel,
+                                                                    float* __restrict__ y, UpfirdnParams p, int tiles_x,
+                                                                    int tiles_y, int total_tiles) {
+    constexpr int TI = kUTI, TILE_F4 = TI * TI * 8;
+    __shared__ float4 tiles[2][TILE_F4];
+    float kreg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) kreg[i] = p.flip ? __ldg(kernel + 15 - i) : __ldg(kernel + i);
+    const int cchunks = p.C >> 5;
+    const int c4 = threadIdx.x & 7, lx = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
+    const int q = lx & 1, mx = lx >> 1;
+    // tile origins are multiples of 16, so parities depend on (py0, px0) only.  Output row Y = y0 + 8*half + 2m + r uses
+    // kernel rows a(r,s) = ((r + 3 - py0) & 1) + 2s at input row (Y + 3 - py0 - a)/2; same for columns with (q, t).
+    int ar[2][2], bt[2], offy[2][2], offx[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            ar[r][sl] = ((r + 3 - p.py0) & 1) + 2 * sl;
+            offy[r][sl] = ((3 - p.py0 + r - ar[r][sl]) >> 1) - ((-p.py0) >> 1);      // relative to the tile's first input row
+        }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        bt[t] = ((q + 3 - p.px0) & 1) + 2 * t;
+        offx[t] = ((3 - p.px0 + q - bt[t]) >> 1) - ((-p.px0) >> 1);
+    }
+    float kk[2][2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int idx = ar[r][sl] * 4 + bt[t];
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v = (i == idx) ? kreg[i] : v;
+                kk[r][sl][t] = v;
+            }
+
+    auto decode = [&](int t, int& b, int& y0, int& x0, int& cc) {
+        cc = t % cchunks; t /= cchunks;
+        x0 = (t % tiles_x) * kUT; t /= tiles_x;
+        y0 = (t % tiles_y) * kUT;
+        b = t / tiles_y;
+    };
+    auto issue = [&](int t, int buf) {
+        int b, y0, x0, cc;
+        decode(t, b, y0, x0, cc);
+        const int ix0 = (x0 - p.px0) >> 1, iy0 = (y0 - p.py0) >> 1;      // floor: first input column / row of the tile
+        const float* xb = x + static_cast<long long>(b) * p.Hi * p.Wi * p.C + cc * 32;
+        for (int idx = threadIdx.x; idx < TILE_F4; idx += 256) {
+            const int cl = idx & 7, pix = idx >> 3;
+            const int px = pix % TI, py = pix / TI;
+            const int gx = ix0 + px, gy = iy0 + py;
+            const bool ok = static_cast<unsigned>(gx) < static_cast<unsigned>(p.Wi) &&
+                            static_cast<unsigned>(gy) < static_cast<unsigned>(p.Hi);
+            const float* src = ok ? xb + (static_cast<long long>(gy) * p.Wi + gx) * p.C + cl * 4 : x;
+            cp_async16(&tiles[buf][idx], src, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    int t = blockIdx.x, buf = 0;
+    if (t < total_tiles) issue(t, 0);
+    for (; t < total_tiles; t += gridDim.x, buf ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tn < total_tiles) { issue(tn, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const float4* tile = tiles[buf];
+        int b, y0, x0, cc;
+        decode(t, b, y0, x0, cc);
+        const int xo = x0 + lx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = i >> 1, r = i & 1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int tt = 0; tt < 2; ++tt) {
+                    const float4 v = tile[((m + 4 * half + offy[r][sl]) * TI + mx + offx[tt]) * 8 + c4];
+                    const float kv = kk[r][sl][tt];
+                    acc.x += kv * v.x; acc.y += kv * v.y; acc.z += kv * v.z; acc.w += kv * v.w;
+                }
+            const int yo = y0 + half * 8 + i;
+            if (xo < p.Wo && yo < p.Ho) {
+                if (p.rtf32) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+                reinterpret_cast<float4*>(y + ((static_cast<long long>(b) * p.Ho + yo) * p.Wo + xo) * p.C + cc * 32)[c4] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace gifb200
 
 using namespace gifb200;
@@ -403,6 +548,16 @@ extern "C" int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y);
     static const bool use_pipe = [] { const char* e = getenv("GIFB200_FIR_PIPE"); return !e || e[0] != '0'; }();
+    if (use_pipe && vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 2 && down == 1 && Ho >= 8 && Wo >= 8 && pad_y0 >= 0 &&
+        pad_x0 >= 0 && pad_y0 <= 3 && pad_x0 <= 3) {
+        const int tiles_x = (Wo + kUT - 1) / kUT, tiles_y = (Ho + kUT - 1) / kUT;
+        const long long tiles = static_cast<long long>(B) * tiles_x * tiles_y * (C / 32);
+        GIFB200_REQUIRE(tiles <= 2147483647LL, GIFB200_E_SHAPE, "upfirdn2d: grid too large");
+        const int ctas = static_cast<int>(tiles < 4LL * kNumSMs ? tiles : 4LL * kNumSMs);
+        upfirdn2d_up2_pipe_kernel<<<ctas, 256, 0, st>>>(x, kernel, y, p, tiles_x, tiles_y, static_cast<int>(tiles));
+        GIFB200_LAUNCH_CHECK("upfirdn2d_up2_pipe_kernel");
+        return GIFB200_OK;
+    }
     if (use_pipe && vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 1 && (down == 1 || down == 2) && Ho >= 4 && Wo >= 4) {
         const int to = down == 1 ? kBT : kDT, ti = down == 1 ? kBTI : kDTI;
         const int tiles_x = (Wo + to - 1) / to, tiles_y = (Ho + to - 1) / to;

@@ -85,3 +85,49 @@ def synthetic_flame_batch(batch, h, w, seed=0, device="cuda"):
     fv = pix[:, faces]          # (B,F,3,3)
     fc = vcol[:, faces]
     return fv.contiguous().to(device), fc.contiguous().to(device)
+
+
+def synthetic_flame_model(seed=11, n_shape=100, n_exp=50):
+    """A FLAME-*shaped* articulated model on the real FLAME topology (the licence-gated generic_model.pkl is absent): the
+    tensors FLAME.__init__ registers (FLAME.py:50-68, 80-86) with the same shapes / meaning, filled deterministically:
+      v_template (V,3); shapedirs (V,3,n_shape+n_exp): the smooth basis of ``_decode``; posedirs (36, V*3): smooth, ~0.3 mm
+      per unit of pose feature; J_regressor (5,V): rows >= 0 summing to 1 (Gaussian windows around 5 joint centres: root,
+      neck, jaw, two eyes); parents [-1,0,1,1,1] (FLAME's kinematic tree); lbs_weights (V,5): softmax of -dist^2 to the
+      joint centres (rows sum to 1); landmark embeddings: 51 static, 79 x 17 dynamic, 68 full (random faces / barycentrics).
+    Everything is float32 CPU tensors; pass to gif_b200.flame.FLAME.from_arrays."""
+    tmpl, faces = flame_topology()
+    V = tmpl.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    nb = n_shape + n_exp
+    freq = (torch.rand(nb, 3, generator=g) * 2 - 1) * 8.0
+    phase = torch.rand(nb, 1, generator=g) * (2 * math.pi)
+    dirs = torch.nn.functional.normalize(torch.randn(nb, 3, generator=g), dim=1)
+    wave = torch.cos(2 * math.pi * (freq @ tmpl.t()) + phase)                         # (nb, V)
+    shapedirs = (0.0005 * wave[:, :, None] * dirs[:, None, :]).permute(1, 2, 0).contiguous()   # (V,3,nb)
+    freq = (torch.rand(36, 3, generator=g) * 2 - 1) * 6.0
+    phase = torch.rand(36, 1, generator=g) * (2 * math.pi)
+    dirs = torch.nn.functional.normalize(torch.randn(36, 3, generator=g), dim=1)
+    wave = torch.cos(2 * math.pi * (freq @ tmpl.t()) + phase)
+    posedirs = (0.0003 * wave[:, :, None] * dirs[:, None, :]).reshape(36, V * 3).contiguous()
+    lo, hi = tmpl.min(0).values, tmpl.max(0).values
+    ext = hi - lo
+    centres = torch.stack([lo + ext * torch.tensor(f) for f in
+                           ([0.5, 0.15, 0.35], [0.5, 0.3, 0.4], [0.5, 0.4, 0.75], [0.33, 0.62, 0.85], [0.67, 0.62, 0.85])])
+    d2 = ((tmpl[None] - centres[:, None]) ** 2).sum(-1)                               # (5,V)
+    jr = torch.exp(-d2 / (2 * (0.02 ** 2)))
+    jr = jr / jr.sum(1, keepdim=True)
+    lbs_weights = torch.softmax(-d2.t() / (2 * (0.03 ** 2)), dim=1).contiguous()     # (V,5)
+    F_ = faces.shape[0]
+
+    def bary(*shape):
+        b = torch.rand(*shape, 3, generator=g) + 0.05
+        return b / b.sum(-1, keepdim=True)
+
+    return {
+        "v_template": tmpl.clone(), "faces": faces.clone(), "shapedirs": shapedirs, "posedirs": posedirs,
+        "J_regressor": jr.contiguous(), "parents": torch.tensor([-1, 0, 1, 1, 1], dtype=torch.long),
+        "lbs_weights": lbs_weights, "n_shape": n_shape, "n_exp": n_exp,
+        "lmk_faces_idx": torch.randint(0, F_, (51,), generator=g), "lmk_bary_coords": bary(51),
+        "dynamic_lmk_faces_idx": torch.randint(0, F_, (79, 17), generator=g), "dynamic_lmk_bary_coords": bary(79, 17),
+        "full_lmk_faces_idx": torch.randint(0, F_, (1, 68), generator=g), "full_lmk_bary_coords": bary(1, 68),
+    }

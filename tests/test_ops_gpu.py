@@ -101,6 +101,26 @@ def test_upfirdn2d_down2_tiled_kernel(cuda, fp32_mode, c, h, w, pad):
     close(nchw(gx), gxo, TOL32, "up2 bwd (down2 kernel, flipped)")
 
 
+@pytest.mark.parametrize("c,h,w", [(32, 21, 19), (64, 16, 40), (32, 5, 6)])
+@pytest.mark.parametrize("pad", [(1, 1), (2, 2), (2, 1)])
+@pytest.mark.parametrize("kind", ["blur", "random"])
+def test_upfirdn2d_blur_tiled_kernel(cuda, fp32_mode, c, h, w, pad, kind):
+    """the pipelined shared-memory 4x4 FIR (C % 32 == 0, up = down = 1): the rank-1 fast path taken for the model's
+    blur kernel and the general path (random asymmetric kernel), ragged tiles, forward and adjoint (flip)."""
+    from gif_b200 import ops
+    k = gu.blur_kernel(4.0) if kind == "blur" else gu.randn((4, 4), 25)
+    x = gu.randn((2, c, h, w), 26)
+    xg = nhwc(x, cuda).requires_grad_(True)
+    y = ops.upfirdn2d(xg, k.to(cuda), 1, 1, pad)
+    xo = x.clone().requires_grad_(True)
+    yo = O.upfirdn2d(xo, k, 1, 1, pad)
+    close(nchw(y), yo, TOL32, "blur fwd")
+    gy = gu.randn(tuple(yo.shape), 27)
+    (gx,) = torch.autograd.grad(y, xg, nhwc(gy, cuda))
+    (gxo,) = torch.autograd.grad(yo, xo, gy)
+    close(nchw(gx), gxo, TOL32, "blur bwd")
+
+
 # ------------------------------------------------------------------------------------------------ small ops
 def test_small_ops_golden(cuda):
     from gif_b200.model import stylegan2_common_layers as cl
