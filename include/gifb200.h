@@ -188,6 +188,20 @@ int gifb200_render_shade(const int32_t* triangle, const float* bary, const float
                          const float* albedo, const float* sh, float* tex, float* nrm, float* cond, int B, int F, int h,
                          int w, int T, gifb200_stream_t stream);
 
+/* FLAME decoder: linear blend skinning, lbs() of my_utils/photometric_optimization/models/lbs.py:141-228 as called by
+ * FLAME.forward (models/FLAME.py:175-216).  betas (B,NB) = [shape | expression], pose (B,NJ*3) axis-angle per joint
+ * (FLAME: NJ = 5 = global, neck, jaw, 2 eyes).  Model tensors prepared once by the host binding: v_template (V,3);
+ * shapedirs_t (NB, V*3) = the reference's shapedirs (V,3,NB) with the coefficient axis first; posedirs ((NJ-1)*9, V*3) as
+ * in the reference; j_template (NJ,3) = J_regressor @ v_template and j_shapedirs (NB, NJ*3) = J_regressor contracted
+ * with shapedirs (the reference regresses the joints from the shaped mesh on every call, lbs.py:180 -- same value, one
+ * reduction over the mesh less); parents (NJ) int32 kinematic tree (entry 0 ignored); lbs_weights (V,NJ).
+ * Outputs: verts (B,V,3); joints (B,NJ,3) posed joint locations (may be NULL).  NJ <= 8, NB <= 1024. */
+size_t gifb200_flame_lbs_workspace_bytes(int B, int NJ);
+int gifb200_flame_lbs(const float* betas, const float* pose, const float* v_template, const float* shapedirs_t,
+                      const float* posedirs, const float* j_template, const float* j_shapedirs, const int32_t* parents,
+                      const float* lbs_weights, float* verts, float* joints, int B, int V, int NB, int NJ, void* ws,
+                      size_t ws_bytes, gifb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

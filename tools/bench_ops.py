@@ -132,6 +132,31 @@ def render():
         note="projection + vertex normals (torch glue on 5023 vertices) + rasterise + fused shade -> tex, normal, cond maps")
 
 
+def flame_pipeline():
+    """FLAME parameters -> LBS (gifb200_flame_lbs) -> projection -> rasterise -> fused shade -> cond map, bs64."""
+    from gif_b200 import flame as gflame
+    from gif_b200.flame_synth import flame_uv, synthetic_flame_model, synthetic_flame_params
+    from gif_b200.render import FlameRenderer
+    b, S = 64, 256
+    fl = gflame.FLAME.from_arrays(synthetic_flame_model()).to(dev)
+    g = torch.Generator().manual_seed(0)
+    shape, exp = torch.randn(b, 100, generator=g).to(dev), torch.randn(b, 50, generator=g).to(dev)
+    pose = ((torch.rand(b, 6, generator=g) * 2 - 1) * torch.tensor([0.2, 0.5, 0.1, 0.3, 0.0, 0.0])).to(dev)
+    _, cam, alb, lights = (t.to(dev) for t in synthetic_flame_params(b, seed=0))
+    uv, uvf = flame_uv()
+    R = FlameRenderer(fl.faces_tensor.cpu(), uv, uvf, image_size=S).to(dev)
+    betas = torch.cat([shape, exp], 1)
+    full_pose = torch.cat([pose[:, :3], torch.zeros(b, 3, device=dev), pose[:, 3:], torch.zeros(b, 6, device=dev)], 1)
+    ms_lbs = timeit(lambda: gflame.lbs(betas, full_pose, fl._model()), flush=True)
+    ms_fwd = timeit(lambda: fl(shape, exp, pose), flush=True)
+    ms_all = timeit(lambda: R.render_tex_and_normal(fl(shape, exp, pose)[0], cam, alb, lights), flush=True)
+    V, NB, P = 5023, 150, 36
+    basis_bytes = (NB + P) * 3 * V * 4 * (b // 8) + b * V * 12          # bases re-read once per 8-sample group (L2 hits)
+    out(bench="flame_lbs_bs64", lbs_kernels_ms=ms_lbs, lbs_decodes_per_s=b / ms_lbs * 1e3, lbs_gbs_incl_l2_rereads=basis_bytes / ms_lbs / 1e6,
+        flame_forward_with_landmarks_ms=ms_fwd, params_to_condition_map_ms=ms_all, condition_maps_per_s=b / ms_all * 1e3,
+        note="FLAME params -> vertices (2 kernels) -> landmarks (torch glue) ; full: + projection, normals, rasterise, shade")
+
+
 def memory_bound():
     x = torch.randn(32, 256, 256, 128, device=dev)
     k = torch.tensor([1., 3., 3., 1.], device=dev)
@@ -170,5 +195,6 @@ if __name__ == "__main__":
     if "raster" in which:
         raster()
         render()
+        flame_pipeline()
     if "memory" in which:
         memory_bound()
