@@ -145,15 +145,22 @@ class FLAME(nn.Module):
                                   self.full_lmk_bary_coords.repeat(B, 1, 1))
 
     @torch.no_grad()
-    def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None):
-        """shape (B,n_shape), expression (B,n_exp), pose (B,6) = [global rotation | jaw] -> vertices (B,V,3),
-        landmarks2d (B,68,3), landmarks3d (B,68,3)   (FLAME.py:175-216)."""
+    def decode_vertices(self, shape_params, expression_params, pose_params, eye_pose_params=None):
+        """The mesh only (what the conditioning render consumes): -> vertices (B,V,3), full pose (B,15)."""
+        require_cuda(shape_params, expression_params, pose_params, eye_pose_params)
         B = shape_params.shape[0]
         if eye_pose_params is None:
             eye_pose_params = self.eye_pose.expand(B, -1)
         betas = torch.cat([shape_params, expression_params], dim=1)
         full_pose = torch.cat([pose_params[:, :3], self.neck_pose.expand(B, -1), pose_params[:, 3:], eye_pose_params], dim=1)
-        vertices, _ = lbs(betas, full_pose, self._model())
+        return lbs(betas, full_pose, self._model())[0], full_pose
+
+    @torch.no_grad()
+    def forward(self, shape_params=None, expression_params=None, pose_params=None, eye_pose_params=None):
+        """shape (B,n_shape), expression (B,n_exp), pose (B,6) = [global rotation | jaw] -> vertices (B,V,3),
+        landmarks2d (B,68,3), landmarks3d (B,68,3)   (FLAME.py:175-216)."""
+        vertices, full_pose = self.decode_vertices(shape_params, expression_params, pose_params, eye_pose_params)
+        B = vertices.shape[0]
         dyn_idx, dyn_bc = self._find_dynamic_lmk_idx_and_bcoords(full_pose.float(), self.dynamic_lmk_faces_idx,
                                                                  self.dynamic_lmk_bary_coords, self.neck_kin_chain)
         idx = torch.cat([dyn_idx, self.lmk_faces_idx[None].expand(B, -1)], 1)

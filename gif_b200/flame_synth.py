@@ -131,3 +131,46 @@ def synthetic_flame_model(seed=11, n_shape=100, n_exp=50):
         "dynamic_lmk_faces_idx": torch.randint(0, F_, (79, 17), generator=g), "dynamic_lmk_bary_coords": bary(79, 17),
         "full_lmk_faces_idx": torch.randint(0, F_, (1, 68), generator=g), "full_lmk_bary_coords": bary(1, 68),
     }
+
+
+def synthetic_texture_data(size=256):
+    """The pre-computed FLAME texture-space table FlameTextureSpace consumes (model/stg2_generator.py:349-354; the
+    reference loads it from the licence-gated ``flame_texture_space_dat_file``): for every texel of the size x size UV
+    atlas covered by a UV triangle, the three mesh VERTEX ids of that triangle (``valid_pixel_3d_faces``) and the
+    barycentric weights of the texel centre (``valid_pixel_b_coords``).  Built here by rasterising the template's real UV
+    layout (tests/golden/flame_template.npz): u -> column, (1 - v) -> row, texel centres at integer + 0.5."""
+    if ("tex", size) in _cache:
+        return _cache[("tex", size)]
+    _, faces = flame_topology()
+    uv, uvf = flame_uv()
+    faces, uv, uvf = faces.numpy(), uv.numpy().astype(np.float64), uvf.numpy()
+    px = np.stack([uv[:, 0] * size, (1.0 - uv[:, 1]) * size], 1)          # texel space, (x, y)
+    tri = px[uvf]                                                         # (F,3,2)
+    owner = -np.ones((size, size), dtype=np.int64)
+    bary = np.zeros((size, size, 3), dtype=np.float64)
+    for f in range(tri.shape[0]):
+        (x0, y0), (x1, y1), (x2, y2) = tri[f]
+        den = (y1 - y2) * (x0 - x2) + (x2 - x1) * (y0 - y2)
+        if abs(den) < 1e-12:
+            continue
+        xa, xb = max(int(np.floor(min(x0, x1, x2) - 0.5)), 0), min(int(np.ceil(max(x0, x1, x2) - 0.5)), size - 1)
+        ya, yb = max(int(np.floor(min(y0, y1, y2) - 0.5)), 0), min(int(np.ceil(max(y0, y1, y2) - 0.5)), size - 1)
+        if xa > xb or ya > yb:
+            continue
+        xs, ys = np.meshgrid(np.arange(xa, xb + 1) + 0.5, np.arange(ya, yb + 1) + 0.5)
+        w0 = ((y1 - y2) * (xs - x2) + (x2 - x1) * (ys - y2)) / den
+        w1 = ((y2 - y0) * (xs - x2) + (x0 - x2) * (ys - y2)) / den
+        w2 = 1.0 - w0 - w1
+        inside = (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
+        sub_o, sub_b = owner[ya:yb + 1, xa:xb + 1], bary[ya:yb + 1, xa:xb + 1]
+        take = inside & (sub_o < 0)
+        sub_o[take] = f
+        sub_b[take] = np.stack([w0, w1, w2], -1)[take]
+    ys, xs = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    valid = np.nonzero(owner.reshape(-1) >= 0)[0]
+    data = {"x_coords": xs.reshape(-1).astype(np.int64), "y_coords": ys.reshape(-1).astype(np.int64),
+            "valid_pixel_ids": valid.astype(np.int64),
+            "valid_pixel_3d_faces": faces[owner.reshape(-1)[valid]].astype(np.int64),
+            "valid_pixel_b_coords": bary.reshape(-1, 3)[valid].astype(np.float32)}
+    _cache[("tex", size)] = data
+    return data

@@ -81,6 +81,47 @@ def main():
         fh.write("\n# oracle/flame_oracle.py vs reference lbs.py / FLAME.py (synthetic FLAME-shaped model, make_flame_golden.py)\n")
         fh.write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    texture_golden(ref_import.load(), m)
+
+
+def texture_golden(R, m):
+    """FlameTextureSpace.compute_texture_map (model/stg2_generator.py:376-421), called UNBOUND on a stand-in object that
+    carries only the table attributes the method reads (the constructor needs the licence-gated FLAME pickle)."""
+    import types
+    from oracle import texture_oracle as TO
+    from gif_b200.flame_synth import synthetic_texture_data
+    td = synthetic_texture_data()
+    lines, out = [], {}
+    for dt, tag in ((torch.float32, "f32"),):          # the reference method is fp32-only (texture_grid is created float32, :403)
+        p = params(3, 77, dt)
+        verts, _, _ = FO.flame_forward(m, p[0], p[1], p[2], p[3], p[4])
+        g = torch.Generator().manual_seed(5)
+        cam = torch.cat([torch.rand(3, 1, generator=g) * 3 + 6, (torch.rand(3, 2, generator=g) * 2 - 1) * 0.03], 1).to(dt)
+        src = (torch.rand(3, 3, 48, 40, generator=g) * 2 - 1).to(dt)
+        tv = TO.batch_orth_proj(verts, cam).clone()
+        tv[:, :, 1:] = -tv[:, :, 1:]
+        vn_ref = R.gen.mesh_and_3d_helpers.vertex_normals(tv.float(), m["faces"][None].expand(3, -1, -1)).to(dt) \
+            if dt == torch.float32 else TO.vertex_normals(tv, m["faces"])      # the reference helper is fp32-only (:19)
+        stand_in = types.SimpleNamespace(
+            x_coords=td["x_coords"], y_coords=td["y_coords"], valid_pixel_ids=td["valid_pixel_ids"],
+            valid_pixel_3d_faces=torch.from_numpy(td["valid_pixel_3d_faces"]),
+            valid_pixel_b_coords=torch.from_numpy(td["valid_pixel_b_coords"]).to(dt))
+        with __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            tex_r, mask_r = R.gen.FlameTextureSpace.compute_texture_map(stand_in, src, verts, vn_ref, camera_params=cam)
+        tex_o, mask_o = TO.compute_texture_map(src, verts, TO.vertex_normals(tv, m["faces"]), cam, td)
+        err = float((tex_o - tex_r).abs().max())
+        mism = int((mask_o != mask_r).sum())
+        assert err < (1e-12 if dt == torch.float64 else 2e-6) and mism == 0, (tag, err, mism)
+        lines.append(f"texture_steal[{tag}] max|oracle - reference| = {err:.3e}, visibility-mask mismatches = {mism}")
+        if dt == torch.float32:
+            out.update(shape=p[0].numpy(), exp=p[1].numpy(), pose=p[2].numpy(), eye=p[3].numpy(), neck=p[4].numpy(),
+                       cam=cam.numpy(), src=src.numpy(), verts=verts.numpy(),
+                       tex_sub=tex_r.numpy()[:, :, ::3, ::3], mask=np.packbits(mask_r.numpy()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "texture_steal.npz"), **out)
+    with open(os.path.join(ROOT, "tests", "golden", "ORACLE_VS_REFERENCE.txt"), "a") as fh:
+        fh.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
 
 
 if __name__ == "__main__":

@@ -75,7 +75,8 @@ def test_flame_params_to_condition_map_on_device(cuda):
     gen = torch.Generator().manual_seed(3)
     shape, exp = torch.randn(B, 100, generator=gen).to(cuda), torch.randn(B, 50, generator=gen).to(cuda)
     pose = ((torch.rand(B, 6, generator=gen) * 2 - 1) * torch.tensor([0.2, 0.5, 0.1, 0.3, 0.0, 0.0])).to(cuda)
-    verts, _, _ = fl(shape, exp, pose)
+    verts, _ = fl.decode_vertices(shape, exp, pose)
+    assert torch.equal(verts, fl(shape, exp, pose)[0])
     _, cam, alb, lights = synthetic_flame_params(B, seed=1)
     uv, uvf = flame_uv()
     R = FlameRenderer(fl.faces_tensor.cpu(), uv, uvf, image_size=128).to(cuda)

@@ -149,7 +149,7 @@ def flame_pipeline():
     full_pose = torch.cat([pose[:, :3], torch.zeros(b, 3, device=dev), pose[:, 3:], torch.zeros(b, 6, device=dev)], 1)
     ms_lbs = timeit(lambda: gflame.lbs(betas, full_pose, fl._model()), flush=True)
     ms_fwd = timeit(lambda: fl(shape, exp, pose), flush=True)
-    ms_all = timeit(lambda: R.render_tex_and_normal(fl(shape, exp, pose)[0], cam, alb, lights), flush=True)
+    ms_all = timeit(lambda: R.render_tex_and_normal(fl.decode_vertices(shape, exp, pose)[0], cam, alb, lights), flush=True)
     V, NB, P = 5023, 150, 36
     basis_bytes = (NB + P) * 3 * V * 4 * (b // 8) + b * V * 12          # bases re-read once per 8-sample group (L2 hits)
     out(bench="flame_lbs_bs64", lbs_kernels_ms=ms_lbs, lbs_decodes_per_s=b / ms_lbs * 1e3, lbs_gbs_incl_l2_rereads=basis_bytes / ms_lbs / 1e6,
