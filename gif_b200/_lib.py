@@ -50,6 +50,8 @@ SIGNATURES = {
     "gifb200_rasterize_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "gifb200_flame_lbs_workspace_bytes": (_sz, [_i, _i]),
     "gifb200_flame_lbs": (_i, [_p] * 11 + [_i] * 4 + [_p, _sz, _p]),
+    "gifb200_texture_steal_fwd": (_i, [_p] * 9 + [_i] * 6 + [_p]),
+    "gifb200_texture_steal_bwd": (_i, [_p] * 7 + [_i] * 6 + [_p]),
 }
 
 

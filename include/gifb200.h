@@ -202,6 +202,20 @@ int gifb200_flame_lbs(const float* betas, const float* pose, const float* v_temp
                       const float* lbs_weights, float* verts, float* joints, int B, int V, int NB, int NJ, void* ws,
                       size_t ws_bytes, gifb200_stream_t stream);
 
+/* Texture stealing, FlameTextureSpace.compute_texture_map (model/stg2_generator.py:376-421): for every texel of the T x T
+ * FLAME UV atlas, bilinear sample (zeros padding, align_corners = False) of the image src (B,H,W,C) channels-last at the
+ * weak-perspective projection (cam (B,3) = scale, tx, ty; y flipped) of the texel's 3-D point on the posed mesh verts
+ * (B,V,3).  Table (shared by the batch): texel_to_valid (T*T) int32, index n into vid / bary or -1; vid (N,3) int32 mesh
+ * vertex ids; bary (N,3).  Texels with n < 0 sample grid (0,0), the image centre, like the reference's zero-initialised
+ * grid.  Outputs tex (B,T,T,C) and, if mask != NULL, mask (B,T,T) uint8 = interpolated normal z < 0 on valid texels
+ * (normals (B,V,3) of the projected mesh) else 0.  _bwd: the adjoint w.r.t. src (g_src (B,H,W,C) is overwritten). */
+int gifb200_texture_steal_fwd(const float* src, const float* verts, const float* normals, const float* cam,
+                              const int32_t* texel_to_valid, const int32_t* vid, const float* bary, float* tex,
+                              unsigned char* mask, int B, int H, int W, int C, int V, int T, gifb200_stream_t stream);
+int gifb200_texture_steal_bwd(const float* g_tex, const float* verts, const float* cam, const int32_t* texel_to_valid,
+                              const int32_t* vid, const float* bary, float* g_src, int B, int H, int W, int C, int V, int T,
+                              gifb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,6 +157,29 @@ def flame_pipeline():
         note="FLAME params -> vertices (2 kernels) -> landmarks (torch glue) ; full: + projection, normals, rasterise, shade")
 
 
+def texture_steal():
+    """FlameTextureSpace.forward on 31 generated 256^2 images (the InterpolatedTextureLoss batch), fwd and fwd+bwd."""
+    from gif_b200 import flame as gflame
+    from gif_b200.flame_synth import synthetic_flame_model, synthetic_texture_data
+    from gif_b200.texture_space import FlameTextureSpace
+    b = 31
+    fl = gflame.FLAME.from_arrays(synthetic_flame_model()).to(dev)
+    ts = FlameTextureSpace(synthetic_texture_data(), flame=fl)
+    g = torch.Generator().manual_seed(0)
+    params = torch.cat([torch.randn(b, 100, generator=g), torch.randn(b, 50, generator=g), (torch.rand(b, 6, generator=g) * 2 - 1) * 0.3,
+                        torch.rand(b, 1, generator=g) * 3 + 6, (torch.rand(b, 2, generator=g) * 2 - 1) * 0.03], 1).to(dev)
+    img = torch.randn(b, 256, 256, 3, device=dev).permute(0, 3, 1, 2).requires_grad_(True)
+    ms_f = timeit(lambda: ts(img.detach(), params), flush=True)
+
+    def fb():
+        tex, _ = ts(img, params)
+        tex.sum().backward()
+    ms_fb = timeit(fb, iters=5, flush=True)
+    nbytes = b * (256 * 256 * 3 * 4 * 2 + 256 * 256)          # image in, texture out, mask out
+    out(bench="texture_steal_31x256x256", fwd_ms=ms_f, fwd_bwd_ms=ms_fb, textures_per_s=b / ms_f * 1e3,
+        fwd_gbs=nbytes / ms_f / 1e6, note="FLAME decode + projection + vertex normals (torch glue) + gifb200_texture_steal_fwd")
+
+
 def memory_bound():
     x = torch.randn(32, 256, 256, 128, device=dev)
     k = torch.tensor([1., 3., 3., 1.], device=dev)
@@ -196,5 +219,6 @@ if __name__ == "__main__":
         raster()
         render()
         flame_pipeline()
+        texture_steal()
     if "memory" in which:
         memory_bound()
