@@ -276,6 +276,23 @@ int pick_block_n(int Co) {
     return 0;
 }
 
+// T2 corner pixel (2*Hi, 2*Wi): only tap (2,2) on input pixel (Hi-1, Wi-1) reaches it.  One warp per (b, o), staged
+// (tf32-rounded) weights like the tensor-core path.
+__global__ void __launch_bounds__(256) t2_corner_kernel(const float* __restrict__ xpix, const float* __restrict__ w22,
+                                                        float* __restrict__ y, int B, long long x_batch_stride, int Ci, int Co,
+                                                        int Ho, int Wo, ConvEpilogue epi) {
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= static_cast<long long>(B) * Co) return;
+    const int b = static_cast<int>(warp / Co), o = static_cast<int>(warp % Co);
+    const float* xv = xpix + b * x_batch_stride;
+    const float* wv = w22 + static_cast<long long>(o) * Ci;
+    float a = 0.f;
+    for (int i = lane; i < Ci; i += 32) a = fmaf(xv[i], wv[i], a);
+    a = warp_sum(a);
+    if (lane == 0) y[((static_cast<long long>(b) * Ho + (Ho - 1)) * Wo + (Wo - 1)) * Co + o] = apply_epilogue(epi, a, o);
+}
+
 void site_grid(int Hi, int Wi, int Ho, int Wo, int mode, int& Hs, int& Ws) {
     if (mode == 2) { Hs = Hi; Ws = Wi; } else { Hs = Ho; Ws = Wo; }
 }
@@ -323,25 +340,6 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     GIFB200_REQUIRE(aligned16(x) && aligned16(y), GIFB200_E_ALIGN, "conv2d_tc: x / y must be 16-byte aligned");
     const int T = k * k;
     float* wst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
-    // T2: the last output row / column (about 1/128 of the pixels, exact fp32 SIMT) runs concurrently on an auxiliary stream
-    // (event fork/join: stream-ordered, capturable in CUDA graphs, no host synchronisation).
-    static cudaStream_t aux = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // forking costs two cross-stream event edges: only worth it when the tensor-core part is long enough to hide the strip
-    const bool fork = mode == 2 && static_cast<long long>(B) * Hi * Wi >= 32768;
-    if (fork) {
-        if (!aux) {
-            if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
-                return fail(GIFB200_E_CUDA, "conv2d_tc: cannot create the auxiliary stream");
-        }
-        cudaEventRecord(ev_fork, st);
-        cudaStreamWaitEvent(aux, ev_fork, 0);
-        int rcs = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, epi, aux);
-        cudaEventRecord(ev_join, aux);
-        if (rcs != GIFB200_OK) { cudaStreamWaitEvent(st, ev_join, 0); return rcs; }
-    }
     {
         const long long total = static_cast<long long>(T) * Co * Ci;
         int blocks = cdiv(total, 256 * 4);
@@ -374,7 +372,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         }
     } else {
         // output (Y,X) = (2y+py, 2x+px), y<Hi, x<Wi; taps with kh%2==py, kw%2==px read input (y+(py-kh)/2, x+(px-kw)/2).
-        // Row Y=2Hi and column X=2Wi are produced by the SIMT strip kernel below.
+        // Row Y=2Hi and column X=2Wi are produced by the two edge launches below.
         p.nphase = 4; p.oys = p.oxs = 2;
         for (int ph = 0; ph < 4; ++ph) {
             const int py = ph >> 1, px = ph & 1;
@@ -418,12 +416,55 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     if (bn == 128) rc = launch<128>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else if (bn == 64) rc = launch<64>(ma, mb, y, p, static_cast<int>(mtiles), st);
     else rc = launch<32>(ma, mb, y, p, static_cast<int>(mtiles), st);
-    if (fork) {
-        cudaError_t e = cudaStreamWaitEvent(st, ev_join, 0);      // join: later work on `st` sees the strip
-        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "conv2d_tc: join", cudaGetErrorString(e));
-    } else if (mode == 2 && rc == GIFB200_OK) {
-        rc = conv2d_simt_strip(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, transposed, epi, st);
+    if (mode != 2 || rc != GIFB200_OK) return rc;
+    // ---- T2 border: output row Y = 2*Hi and column X = 2*Wi (the sites y = Hi / x = Wi that the power-of-two site grid does
+    // not cover).  Row Y = 2*Hi only sees kernel row kh = 2 applied to input row Hi-1: a 1-D transposed convolution along x;
+    // likewise the column along y with kw = 2.  Both run through the SAME tensor-core kernel on 1-row / 1-column views of
+    // the input (two more launches of ~1/64 of the main work each); the single corner pixel is a dot product per (b, o).
+    // (Until round 1 this border was an fp32 SIMT strip kernel on an auxiliary stream: 0.35 ms per large layer, and it
+    // competed with the persistent tensor-core CTAs for SMs.)
+    for (int edge = 0; edge < 2 && rc == GIFB200_OK; ++edge) {
+        const bool row = edge == 0;
+        TcParams q;
+        memset(&q, 0, sizeof(q));
+        q.B = B; q.Ci = Ci; q.Co = Co; q.Ho = Ho; q.Wo = Wo; q.epi = epi;
+        q.Hs = row ? 1 : Hi; q.Ws = row ? Wi : 1;
+        q.wt = q.Ws < 128 ? q.Ws : 128;
+        q.ht = (128 / q.wt) < q.Hs ? (128 / q.wt) : q.Hs;
+        q.nt = 128 / (q.wt * q.ht);
+        q.tiles_x = q.Ws / q.wt; q.tiles_y = q.Hs / q.ht;
+        const long long mt_e = static_cast<long long>(q.tiles_x) * q.tiles_y * ((B + q.nt - 1) / q.nt);
+        q.s2 = 0; q.in_sy = 1; q.nphase = 2; q.oys = q.oxs = 2;
+        for (int ph = 0; ph < 2; ++ph) {          // parity along the strip
+            q.phase_oy0[ph] = row ? 2 * Hi : ph;
+            q.phase_ox0[ph] = row ? ph : 2 * Wi;
+            int n = 0;
+            for (int kk = ph; kk < 3; kk += 2) {   // the kernel index along the strip with the right parity
+                q.tap_w[ph][n] = row ? (2 * 3 + kk) : (kk * 3 + 2);
+                q.tap_dy[ph][n] = row ? 0 : (ph - kk) / 2;
+                q.tap_dx[ph][n] = row ? (ph - kk) / 2 : 0;
+                ++n;
+            }
+            q.phase_ntaps[ph] = n;
+        }
+        CUtensorMap me;
+        const float* base = x + (row ? static_cast<long long>(Hi - 1) * Wi * Ci : static_cast<long long>(Wi - 1) * Ci);
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(row ? Wi : 1),
+                                    static_cast<cuuint64_t>(row ? 1 : Hi), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Wi) * Ci * 4,
+                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(q.wt), static_cast<cuuint32_t>(q.ht), static_cast<cuuint32_t>(q.nt)};
+        rc = encode_map(&me, base, 4, dims, strides, box);
+        if (rc != GIFB200_OK) return rc;
+        if (bn == 128) rc = launch<128>(me, mb, y, q, static_cast<int>(mt_e), st);
+        else if (bn == 64) rc = launch<64>(me, mb, y, q, static_cast<int>(mt_e), st);
+        else rc = launch<32>(me, mb, y, q, static_cast<int>(mt_e), st);
     }
+    if (rc != GIFB200_OK) return rc;
+    t2_corner_kernel<<<cdiv(static_cast<long long>(B) * Co * 32, 256), 256, 0, st>>>(
+        x + (static_cast<long long>(Hi - 1) * Wi + (Wi - 1)) * Ci, wst + static_cast<long long>(8) * Co * Ci, y, B,
+        static_cast<long long>(Hi) * Wi * Ci, Ci, Co, Ho, Wo, epi);
+    GIFB200_LAUNCH_CHECK("t2_corner_kernel");
     return rc;
 }
 
