@@ -315,7 +315,10 @@ static long long wgrad_splits(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int
     const int bn = pick_bn(Cb);
     const bool stack = (Cs == 32 && mode == 0 && k == 3);
     const long long base_ctas = stack ? (Cb / bn) : static_cast<long long>(Cs / 128) * (Cb / bn) * k;
-    long long splits = (kNumSMs + base_ctas - 1) / base_ctas;
+    // ONE wave: the kernel runs one CTA per SM (175-198 KB of shared memory), so the grid must not exceed the SM count.
+    // (Rounding the split count up gave 150 / 156 / 192 CTAs on 148 SMs: a second wave of 2-44 stragglers doubled the
+    // kernel time -- ncu run 33: tensor pipe busy 58% on the busiest SM but 30% on average.)
+    long long splits = kNumSMs / base_ctas;
     if (splits > units) splits = units;
     if (splits < 1) splits = 1;
     if (units_out) *units_out = units;
