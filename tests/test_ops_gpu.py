@@ -293,3 +293,27 @@ def test_fused_tail_and_scale_backward(cuda, fp32_mode, c):
     for name, g1, g2, r in zip(("acc", "demod", "noise", "bias", "style"), ours(False), ours(True), ref):
         close(g1, r, TOL32, f"fused first-order grad[{name}]")
         close(g2, r, TOL32, f"closed-set grad[{name}]")
+
+
+@pytest.mark.parametrize("c", [32, 64, 128, 512, 20])
+def test_torgb_kernels(cuda, fp32_mode, c):
+    """ToRGB contraction y[b,p,k] = sum_i x[b,p,i] ws[b,k,i]: the 16-byte kernels (8 / 16 / 32 channel lanes, several
+    channel chunks per lane at C = 512, ragged pixel counts) and the scalar fallback; forward, both gradients, and the
+    second derivative closure, against torch einsum."""
+    from gif_b200 import ops
+    b, h, w = 3, 7, 9
+    x = gu.randn((b, h, w, c), 41).to(cuda).requires_grad_(True)
+    ws = gu.randn((b, 3, c), 42).to(cuda).requires_grad_(True)
+    gy = gu.randn((b, h, w, 3), 43).to(cuda)
+    y = ops.torgb(x, ws)
+    xr, wr = x.detach().clone().requires_grad_(True), ws.detach().clone().requires_grad_(True)
+    yr = torch.einsum("bhwi,bki->bhwk", xr, wr)
+    close(y, yr, TOL32, "torgb fwd")
+    gx, gw = torch.autograd.grad(y, (x, ws), gy, create_graph=True)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy, create_graph=True)
+    close(gx, gxr, TOL32, "torgb grad x")
+    close(gw, gwr, TOL32, "torgb grad ws")
+    v = gu.randn((b, h, w, c), 44).to(cuda)
+    (g2,) = torch.autograd.grad((gx * v).sum(), ws)
+    (g2r,) = torch.autograd.grad((gxr * v).sum(), wr)
+    close(g2, g2r, TOL32, "torgb second derivative")
