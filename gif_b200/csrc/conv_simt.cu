@@ -10,24 +10,16 @@ namespace gifb200 {
 
 struct ConvParams {
     int B, Hi, Wi, Ci, Ho, Wo, Co, k, flip;
-    long long M;  // number of output pixels this launch produces (B*Ho*Wo, or B*(Wo+Ho-1) in strip mode)
-    int strip;    // 1: only the last output row and the last output column (border strip of a T2 convolution)
+    long long M;  // number of output pixels (B*Ho*Wo)
     ConvEpilogue epi;
 };
 
 // m-th output pixel of the launch -> (b, yo, xo)
 __device__ __forceinline__ void decode_pixel(const ConvParams& p, long long m, int& b, int& yo, int& xo) {
-    if (!p.strip) {
-        xo = static_cast<int>(m % p.Wo);
-        const long long r = m / p.Wo;
-        yo = static_cast<int>(r % p.Ho);
-        b = static_cast<int>(r / p.Ho);
-    } else {
-        const int per = p.Wo + p.Ho - 1;
-        b = static_cast<int>(m / per);
-        const int idx = static_cast<int>(m % per);
-        if (idx < p.Wo) { yo = p.Ho - 1; xo = idx; } else { xo = p.Wo - 1; yo = idx - p.Wo; }
-    }
+    xo = static_cast<int>(m % p.Wo);
+    const long long r = m / p.Wo;
+    yo = static_cast<int>(r % p.Ho);
+    b = static_cast<int>(r / p.Ho);
 }
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -223,29 +215,12 @@ static int check_conv_shape(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int C
     return GIFB200_OK;
 }
 
-static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
-                            int Co, int k, int mode, int flip, int transposed, int strip, const ConvEpilogue& epi,
-                            cudaStream_t st);
-
 int conv2d_simt(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
                 int mode, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st) {
-    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, flip, transposed, 0, epi, st);
-}
-
-// last output row + last output column of a T2 convolution (the part the tcgen05 phase kernels do not cover)
-int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                      int k, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st) {
-    return conv2d_simt_impl(x, w, y, B, Hi, Wi, Ci, Ho, Wo, Co, k, 2, flip, transposed, 1, epi, st);
-}
-
-static int conv2d_simt_impl(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
-                            int Co, int k, int mode, int flip, int transposed, int strip, const ConvEpilogue& epi,
-                            cudaStream_t st) {
     int rc = check_conv_shape(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
     if (rc != GIFB200_OK) return rc;
     if (B == 0) return GIFB200_OK;
-    ConvParams p{B, Hi, Wi, Ci, Ho, Wo, Co, k, flip,
-                 strip ? static_cast<long long>(B) * (Wo + Ho - 1) : static_cast<long long>(B) * Ho * Wo, strip, epi};
+    ConvParams p{B, Hi, Wi, Ci, Ho, Wo, Co, k, flip, static_cast<long long>(B) * Ho * Wo, epi};
     const long long mb = (p.M + BM - 1) / BM;
     GIFB200_REQUIRE(mb <= 2147483647LL && cdiv(Co, BN) <= 65535, GIFB200_E_SHAPE, "conv2d: grid too large");
     dim3 grid(static_cast<unsigned>(mb), cdiv(Co, BN));

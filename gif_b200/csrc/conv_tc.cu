@@ -23,9 +23,6 @@
 
 namespace gifb200 {
 
-int conv2d_simt_strip(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                      int k, int flip, int transposed, const ConvEpilogue& epi, cudaStream_t st);
-
 namespace {
 
 constexpr int kStages = 3;

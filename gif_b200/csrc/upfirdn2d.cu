@@ -1,7 +1,5 @@
 // upfirdn2d: zero-insert upsample, pad/crop, small FIR, decimate -- one pass, channels-last.
 // HBM-bound: algorithmic bytes = input + output (taps are re-read from L1/L2, never from HBM).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace gifb200 {
@@ -119,145 +117,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_blur4_kernel(const float* __res
     }
 }
 
-// Shared-memory tiled version of the same case for C % 32 == 0: a CTA stages the (16+3) x (16+3) input pixels x 32
-// channels its 16 x 16 output tile needs (46 KB, read amplification 1.41x instead of 16x through L1/L2), then every
-// thread produces a column of 8 outputs x 4 channels from shared memory with the sliding-window scheme above
-// (11 rows x 4 taps = 44 conflict-free 16-byte smem reads for 8 outputs).
+// Tile geometry of the shared-memory FIR kernels below (C % 32 == 0): 16 x 16 outputs from (16+3)^2 input pixels x 32
+// channels (46 KB; read amplification 1.41x instead of 16x through L1/L2) for up = down = 1.
 constexpr int kBT = 16;                 // output tile edge
 constexpr int kBTI = kBT + 3;           // input tile edge
-__global__ void __launch_bounds__(256) upfirdn2d_blur4_smem_kernel(const float* __restrict__ x,
-                                                                   const float* __restrict__ kernel,
-                                                                   float* __restrict__ y, UpfirdnParams p, int tiles_x,
-                                                                   int tiles_y) {
-    __shared__ float4 tile[kBTI * kBTI * 8];
-    __shared__ float sk[16];
-    if (threadIdx.x < 16) {
-        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
-        sk[threadIdx.x] = p.flip ? kernel[(3 - a) * 4 + (3 - b)] : kernel[threadIdx.x];
-    }
-    const int cchunks = p.C >> 5;
-    int t = blockIdx.x;
-    const int cc = t % cchunks; t /= cchunks;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int b = t / tiles_y;
-    const int x0 = tx * kBT, y0 = ty * kBT;
-    const int ix0 = x0 - p.px0, iy0 = y0 - p.py0;
-    const float* xb = x + static_cast<long long>(b) * p.Hi * p.Wi * p.C + cc * 32;
-    for (int idx = threadIdx.x; idx < kBTI * kBTI * 8; idx += 256) {
-        const int c4 = idx & 7, pix = idx >> 3;
-        const int px = pix % kBTI, py = pix / kBTI;
-        const int gx = ix0 + px, gy = iy0 + py;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gx >= 0 && gx < p.Wi && gy >= 0 && gy < p.Hi)
-            v = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<long long>(gy) * p.Wi + gx) * p.C) + c4);
-        tile[idx] = v;
-    }
-    __syncthreads();
-    const int c4 = threadIdx.x & 7, lx = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;
-    constexpr int R = 8;
-    float4 acc[R];
-#pragma unroll
-    for (int i = 0; i < R; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < R + 3; ++j) {
-        const int row = half * R + j;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const float4 v = tile[(row * kBTI + lx + 3 - bb) * 8 + c4];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int a = 3 - (j - i);
-                if (a < 0 || a > 3) continue;
-                const float kv = sk[a * 4 + bb];
-                acc[i].x += kv * v.x; acc[i].y += kv * v.y; acc[i].z += kv * v.z; acc[i].w += kv * v.w;
-            }
-        }
-    }
-    const int xo = x0 + lx;
-    if (xo >= p.Wo) return;
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-        const int yo = y0 + half * R + i;
-        if (yo >= p.Ho) break;
-        float4 o = acc[i];
-        if (p.rtf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        reinterpret_cast<float4*>(y + ((static_cast<long long>(b) * p.Ho + yo) * p.Wo + xo) * p.C + cc * 32)[c4] = o;
-    }
-}
-
-// Shared-memory tiled 4x4 FIR with decimation by 2 (D's blur -> 1x1 stride-2 skip, evaluated as upfirdn2d(down=2), and
-// the adjoint of every up=2 call) for C % 32 == 0: a CTA stages the (2*8+2)^2 input pixels x 32 channels of its 8 x 8
-// output tile (41 KB; read amplification 1.27x instead of 4x through L1/L2); every thread produces two vertically
-// adjacent outputs x 4 channels from 6 input rows x 4 taps.
+// Decimation by 2 (D's blur -> 1x1 stride-2 skip evaluated as upfirdn2d(down=2), adjoints of up=2): 8 x 8 outputs from
+// (2*8+2)^2 input pixels x 32 channels (41 KB; read amplification 1.27x instead of 4x).
 constexpr int kDT = 8;                  // output tile edge
 constexpr int kDTI = 2 * kDT + 2;       // input tile edge
-__global__ void __launch_bounds__(256) upfirdn2d_down2_smem_kernel(const float* __restrict__ x,
-                                                                   const float* __restrict__ kernel,
-                                                                   float* __restrict__ y, UpfirdnParams p, int tiles_x,
-                                                                   int tiles_y) {
-    __shared__ float4 tile[kDTI * kDTI * 8];
-    __shared__ float sk[16];
-    if (threadIdx.x < 16) {
-        const int a = threadIdx.x >> 2, b = threadIdx.x & 3;
-        sk[threadIdx.x] = p.flip ? kernel[(3 - a) * 4 + (3 - b)] : kernel[threadIdx.x];
-    }
-    const int cchunks = p.C >> 5;
-    int t = blockIdx.x;
-    const int cc = t % cchunks; t /= cchunks;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int b = t / tiles_y;
-    const int x0 = tx * kDT, y0 = ty * kDT;
-    const int ix0 = 2 * x0 - p.px0, iy0 = 2 * y0 - p.py0;
-    const float* xb = x + static_cast<long long>(b) * p.Hi * p.Wi * p.C + cc * 32;
-    for (int idx = threadIdx.x; idx < kDTI * kDTI * 8; idx += 256) {
-        const int c4 = idx & 7, pix = idx >> 3;
-        const int px = pix % kDTI, py = pix / kDTI;
-        const int gx = ix0 + px, gy = iy0 + py;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gx >= 0 && gx < p.Wi && gy >= 0 && gy < p.Hi)
-            v = __ldg(reinterpret_cast<const float4*>(xb + (static_cast<long long>(gy) * p.Wi + gx) * p.C) + c4);
-        tile[idx] = v;
-    }
-    __syncthreads();
-    float kreg[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) kreg[i] = sk[i];
-    const int c4 = threadIdx.x & 7, lx = (threadIdx.x >> 3) & 7, rp = threadIdx.x >> 6;   // rows 2rp, 2rp+1 of the tile
-    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-    // out[yo] = sum_a K[a] * in[2*yo + 3 - a - py0]: local input row j (0..5, relative to 2*(2rp)) feeds
-    // output 0 with a = 3 - j (j <= 3) and output 1 with a = 5 - j (j >= 2)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const int row = 4 * rp + j;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const float4 v = tile[(row * kDTI + 2 * lx + 3 - bb) * 8 + c4];
-            if (j <= 3) {
-                const float kv = kreg[(3 - j) * 4 + bb];
-                acc0.x += kv * v.x; acc0.y += kv * v.y; acc0.z += kv * v.z; acc0.w += kv * v.w;
-            }
-            if (j >= 2) {
-                const float kv = kreg[(5 - j) * 4 + bb];
-                acc1.x += kv * v.x; acc1.y += kv * v.y; acc1.z += kv * v.z; acc1.w += kv * v.w;
-            }
-        }
-    }
-    const int xo = x0 + lx;
-    if (xo >= p.Wo) return;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int yo = y0 + 2 * rp + i;
-        if (yo >= p.Ho) break;
-        float4 o = i ? acc1 : acc0;
-        if (p.rtf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        reinterpret_cast<float4*>(y + ((static_cast<long long>(b) * p.Ho + yo) * p.Wo + xo) * p.C + cc * 32)[c4] = o;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ pipelined 4x4 FIR
-// Persistent, double-buffered version of the two tiled kernels above (C % 32 == 0, 4x4 kernel, up = 1, down = 1 or 2).
+// Persistent, double-buffered shared-memory FIR (C % 32 == 0, 4x4 kernel, up = 1, down = 1 or 2).
 // ncu on the single-buffered blur (profiles/r01_ncu_upfirdn_blur.md): DRAM traffic is already algorithmic (1.07 GB in,
 // 1.04 GB out) but the kernel sits at 3.0 TB/s with `long_scoreboard` as the top stall -- a CTA loads its tile, waits,
 // computes, and 4 CTAs per SM (register + smem limit) do not keep enough bytes in flight.  Here a CTA walks a list of
@@ -547,8 +416,7 @@ extern "C" int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, 
     UpfirdnParams p{B, Hi, Wi, C, Ho, Wo, kh, kw, up, down, pad_y0, pad_x0, flip, round_tf32};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(y);
-    static const bool use_pipe = [] { const char* e = getenv("GIFB200_FIR_PIPE"); return !e || e[0] != '0'; }();
-    if (use_pipe && vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 2 && down == 1 && Ho >= 8 && Wo >= 8 && pad_y0 >= 0 &&
+    if (vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 2 && down == 1 && Ho >= 8 && Wo >= 8 && pad_y0 >= 0 &&
         pad_x0 >= 0 && pad_y0 <= 3 && pad_x0 <= 3) {
         const int tiles_x = (Wo + kUT - 1) / kUT, tiles_y = (Ho + kUT - 1) / kUT;
         const long long tiles = static_cast<long long>(B) * tiles_x * tiles_y * (C / 32);
@@ -558,7 +426,7 @@ extern "C" int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, 
         GIFB200_LAUNCH_CHECK("upfirdn2d_up2_pipe_kernel");
         return GIFB200_OK;
     }
-    if (use_pipe && vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 1 && (down == 1 || down == 2) && Ho >= 4 && Wo >= 4) {
+    if (vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 1 && (down == 1 || down == 2) && Ho >= 4 && Wo >= 4) {
         const int to = down == 1 ? kBT : kDT, ti = down == 1 ? kBTI : kDTI;
         const int tiles_x = (Wo + to - 1) / to, tiles_y = (Ho + to - 1) / to;
         const long long tiles = static_cast<long long>(B) * tiles_x * tiles_y * (C / 32);
@@ -578,22 +446,6 @@ extern "C" int gifb200_upfirdn2d(const float* x, const float* kernel, float* y, 
         else
             upfirdn2d_fir4_pipe_kernel<2><<<ctas, 256, smem, st>>>(x, kernel, y, p, tiles_x, tiles_y, static_cast<int>(tiles));
         GIFB200_LAUNCH_CHECK("upfirdn2d_fir4_pipe_kernel");
-        return GIFB200_OK;
-    }
-    if (vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 1 && down == 1 && Ho >= 8 && Wo >= 8) {
-        const int tiles_x = (Wo + kBT - 1) / kBT, tiles_y = (Ho + kBT - 1) / kBT;
-        const long long ctas = static_cast<long long>(B) * tiles_x * tiles_y * (C / 32);
-        GIFB200_REQUIRE(ctas <= 2147483647LL, GIFB200_E_SHAPE, "upfirdn2d: grid too large");
-        upfirdn2d_blur4_smem_kernel<<<static_cast<int>(ctas), 256, 0, st>>>(x, kernel, y, p, tiles_x, tiles_y);
-        GIFB200_LAUNCH_CHECK("upfirdn2d_blur4_smem_kernel");
-        return GIFB200_OK;
-    }
-    if (vec && C % 32 == 0 && kh == 4 && kw == 4 && up == 1 && down == 2 && Ho >= 4 && Wo >= 4) {
-        const int tiles_x = (Wo + kDT - 1) / kDT, tiles_y = (Ho + kDT - 1) / kDT;
-        const long long ctas = static_cast<long long>(B) * tiles_x * tiles_y * (C / 32);
-        GIFB200_REQUIRE(ctas <= 2147483647LL, GIFB200_E_SHAPE, "upfirdn2d: grid too large");
-        upfirdn2d_down2_smem_kernel<<<static_cast<int>(ctas), 256, 0, st>>>(x, kernel, y, p, tiles_x, tiles_y);
-        GIFB200_LAUNCH_CHECK("upfirdn2d_down2_smem_kernel");
         return GIFB200_OK;
     }
     if (vec && kh == 4 && kw == 4 && up == 1 && down == 1 && Ho >= 4) {
