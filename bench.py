@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-ppl-extra", action="store_true", help="skip the additional measurement without the PPL term")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--texture-loss", action="store_true",
+                    help="also time the step of the flagship reference run: no PPL, + texture-space interpolation loss")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -210,6 +212,9 @@ def main():
              torch.rand(B, 6, RES, RES, generator=gen).mul_(2).sub_(1).pin_memory(),
              torch.randint(0, VOCAB, (B,), generator=gen).pin_memory()) for _ in range(n_host)]
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    # FLAME labels [shape 100 | exp 50 | pose 6 | cam 3] for the optional texture-interpolation term (random FLAME params)
+    flm = torch.cat([torch.randn(B, 150, generator=gen), (torch.rand(B, 6, generator=gen) * 2 - 1) * torch.tensor([0.2, 0.5, 0.1, 0.3, 0.02, 0.02]),
+                     torch.rand(B, 1, generator=gen) * 3 + 7, (torch.rand(B, 2, generator=gen) * 2 - 1) * 0.02], 1).to(dev)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     # R1 must fall inside every timed window: start the iteration counter so that the window contains
     # ceil(K/16) penalty iterations, the same share as in the reference's loop.
@@ -224,7 +229,7 @@ def main():
                     real, cond, idx = (t.to(dev, non_blocking=True) for t in hb)
             else:
                 real, cond, idx = resident[s % n_host]
-            out = trainer.train_iteration(real, cond, idx)
+            out = trainer.train_iteration(real, cond, idx, flm if trainer.interp_tex_loss is not None else None)
             if e2e:
                 out = (out[0].item(), out[1].item())      # device -> host read of the step's result
         return out
@@ -319,6 +324,26 @@ def main():
                             "ms_per_step": ms_np / args.steps}
         except Exception as e:
             extra_no_ppl = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+    extra_tex = None
+    if args.texture_loss:
+        # the flagship reference configuration (configurations.py:217, run 29): no PPL, + the texture-space interpolation
+        # loss of train.py:224-238 (31 interpolated FLAME parameter sets -> condition renders -> one more generator
+        # forward/backward -> texture stealing -> pairwise loss), FLAME model data synthetic
+        trainer.ppl = None
+        trainer._graphs = None
+        try:
+            trainer.interp_tex_loss = trainer._build_texture_loss(dev, B)
+            trainer.iteration = 13
+            run(3, False)
+            if not args.no_graph:
+                trainer.capture(B, RES)
+                trainer.iteration = 14
+                run(2, False)
+            ms_t = timed(args.steps, False)
+            extra_tex = {"value": world * B * args.steps / (ms_t / 1000.0), "unit": "images/sec", "ms_per_step": ms_t / args.steps}
+        except Exception as e:
+            extra_tex = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        trainer.interp_tex_loss = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,7 +403,8 @@ def main():
                        "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}", "cuda_graph": graph_note,
                        "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb,
-            "same_step_without_path_length_reg": extra_no_ppl}
+            "same_step_without_path_length_reg": extra_no_ppl,
+            "same_step_with_texture_interpolation_loss_instead_of_ppl": extra_tex}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -126,6 +126,9 @@ class InterpolatedTextureLoss:
     """
 
     def __init__(self, max_images_in_batch, flm_tex_dec, render_condition, face_region_only_mask, rng=None):
+        """``rng``: a numpy-RandomState-like object (default ``numpy.random``, as the reference) for the pair choice and
+        the shared identity; ``rng="device"`` draws both with torch on the device instead, which keeps the whole term
+        capturable in a CUDA graph (host random numbers would be frozen into the graph)."""
         self.flm_tex_dec = flm_tex_dec
         self.render_condition = render_condition
         self.face_region_only_mask = face_region_only_mask
@@ -146,6 +149,20 @@ class InterpolatedTextureLoss:
         """losses.py:161-176."""
         textures, tx_masks, _ = self.get_image_and_textures(alpha, flame_batch, generator, max_ids, normal_maps_as_cond,
                                                             rendered_flame_as_condition, step, use_posed_constant_input)
+        if isinstance(self.rng, str):       # "device": same arithmetic, batched over the chosen pairs
+            dev = textures.device
+            if getattr(self, "_pairs_dev", None) is None or self._pairs_dev.device != dev:
+                self._pairs_dev = torch.as_tensor(self.pairs, device=dev)      # cached: no host copy inside a graph capture
+            pairs = self._pairs_dev
+            sel = torch.randperm(len(self.pairs), device=dev)[:self.max_num]
+            i, j = pairs[sel, 0], pairs[sel, 1]
+            common = (tx_masks[j] * tx_masks[i]).to(textures.dtype)
+            m = self.face_region_only_mask.to(dev)
+            if m.shape[-1] != textures.shape[-1]:
+                m = torch.nn.functional.interpolate(m, size=textures.shape[-2:], mode="bilinear", align_corners=False)
+                self.face_region_only_mask = m
+            per_pair = (torch.sigmoid(torch.pow(textures[i] * common - textures[j] * common, 2)) * m[0]).mean(dim=(1, 2, 3))
+            return 16 * per_pair.sum() / self.max_num
         sel = self.rng.choice(len(self.pairs), self.max_num, replace=False)
         loss = 0
         for i, j in self.pairs[sel]:
@@ -167,7 +184,10 @@ class InterpolatedTextureLoss:
             gen_in = cond[:, 3:]
         else:
             gen_in = flame_batch
-        fixed = torch.ones(flame_batch.shape[0], dtype=torch.long, device=flame_batch.device) * int(self.rng.randint(0, max_ids))
+        if isinstance(self.rng, str):
+            fixed = torch.randint(0, max_ids, (1,), device=flame_batch.device).expand(flame_batch.shape[0])
+        else:
+            fixed = torch.ones(flame_batch.shape[0], dtype=torch.long, device=flame_batch.device) * int(self.rng.randint(0, max_ids))
         pose = flame_batch[:, 150:153] if use_posed_constant_input else None
         generated_image = generator(gen_in, pose=pose, step=step, alpha=alpha, input_indices=fixed)[-1]
         textures, tx_masks = self.flm_tex_dec(generated_image, flame_batch)

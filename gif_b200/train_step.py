@@ -38,7 +38,8 @@ def accumulate(model1, model2, decay=0.999):
 
 
 class GifTrainer:
-    def __init__(self, device, resolution=256, vocab=70_000, r1_every=16, ppl=False, world_size=1, seed=0):
+    def __init__(self, device, resolution=256, vocab=70_000, r1_every=16, ppl=False, world_size=1, seed=0,
+                 texture_loss=False):
         torch.manual_seed(seed)
         self.device = device
         self.step_idx = int(math.log2(resolution)) - 2                           # train.py:387
@@ -58,7 +59,35 @@ class GifTrainer:
         self.ppl = losses.PathLengthRegularizor() if ppl else None
         self.iteration = 0
         self._graphs = None
+        self.vocab = vocab
+        # texture_loss: False | True (per-GPU batch 32) | the per-GPU batch size (max_images_in_batch, train.py:59-60)
+        self.interp_tex_loss = self._build_texture_loss(device, 32 if texture_loss is True else int(texture_loss)) if texture_loss else None
         requires_grad(self.generator, False)
+
+    def _build_texture_loss(self, device, max_images_in_batch):
+        """train.py:57-60 + 224-238 (apply_texture_space_interpolation_loss, enabled in the flagship run,
+        configurations.py:217): FLAME decoder, condition renderer, texture space and the pairwise loss, all on the device.
+        The licence-gated model files are replaced by the synthetic FLAME-shaped model (gif_b200/flame_synth.py)."""
+        from .flame import FLAME
+        from .flame_synth import flame_uv, synthetic_flame_model, synthetic_flame_params, synthetic_texture_data
+        from .render import FlameRenderer
+        from .texture_space import FlameTextureSpace, InterpolatedTextureLoss
+        flame = FLAME.from_arrays(synthetic_flame_model()).to(device)
+        uv, uvf = flame_uv()
+        renderer = FlameRenderer(flame.faces_tensor.cpu(), uv, uvf, image_size=256).to(device)
+        _, _, albedo, lights = synthetic_flame_params(1, seed=0)
+        albedo, lights = albedo.to(device), lights.to(device)
+
+        def render_condition(flame_batch):          # losses.py:186-221 (159-parameter layout): texture render + normal map
+            n = flame_batch.shape[0]
+            verts, _ = flame.decode_vertices(flame_batch[:, :100].float(), flame_batch[:, 100:150].float(),
+                                             flame_batch[:, 150:156].float())
+            return renderer.render_tex_and_normal(verts, flame_batch[:, 156:159].float().contiguous(),
+                                                  albedo.expand(n, -1, -1, -1), lights.expand(n, -1, -1))[2]
+        yy, xx = torch.meshgrid(torch.linspace(-1, 1, 256), torch.linspace(-1, 1, 256), indexing="ij")
+        region = ((xx / 0.8) ** 2 + (yy / 0.9) ** 2 < 1).float()[None, None].to(device)      # stand-in for face_region_mask_file
+        return InterpolatedTextureLoss(max_images_in_batch, FlameTextureSpace(synthetic_texture_data(), flame=flame), render_condition,
+                                       region, rng="device")
 
     # ------------------------------------------------------------------------------------------- CUDA graphs
     def capture(self, batch, resolution):
@@ -75,6 +104,8 @@ class GifTrainer:
         self._static = (torch.zeros(batch, 3, resolution, resolution, device=dev),
                         torch.zeros(batch, 6, resolution, resolution, device=dev),
                         torch.zeros(batch, dtype=torch.long, device=dev))
+        if self.interp_tex_loss is not None:
+            self._static = self._static + (torch.zeros(batch, 159, device=dev),)
         graphs, pool = {}, None
         self.graph_launches = {}
         torch.cuda.synchronize()
@@ -84,21 +115,26 @@ class GifTrainer:
             for seg in (self._seg1, self._seg2, self._seg3):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
-                    seg(state, *self._static, with_r1)
+                    if seg == self._seg2:
+                        seg(state, *self._static[:3], with_r1, *self._static[3:])
+                    else:
+                        seg(state, *self._static[:3], with_r1)
                 pool = g.pool()
                 segs.append(g)
             self.graph_launches[with_r1] = _lib.launch_count() - n0      # gif_b200 kernel nodes per replayed iteration
             graphs[with_r1] = (segs, (state["d_loss"], state["g_loss"]))
         self._graphs = graphs
 
-    def train_iteration(self, real_image, flm_rndr, input_indices):
+    def train_iteration(self, real_image, flm_rndr, input_indices, flm_lbls=None):
         """real_image (B,3,R,R) in [-1,1], flm_rndr (B,6,R,R) in [-1,1], input_indices (B,) int64 -- device tensors (or
-        pinned host tensors when CUDA graphs are active).  Returns (d_loss, g_loss) as 0-d device tensors."""
+        pinned host tensors when CUDA graphs are active); flm_lbls (B,159) FLAME labels [shape|exp|pose|cam], needed only
+        with ``texture_loss=True``.  Returns (d_loss, g_loss) as 0-d device tensors."""
+        extra = () if self.interp_tex_loss is None else (flm_lbls,)
         with_r1 = (self.iteration + 1) % self.r1_every == 0                       # train.py:145
         self.iteration += 1
         if self._graphs is not None:
             self.replayed_launches = getattr(self, "replayed_launches", 0) + self.graph_launches[with_r1]
-            for dst, src in zip(self._static, (real_image, flm_rndr, input_indices)):
+            for dst, src in zip(self._static, (real_image, flm_rndr, input_indices) + extra):
                 dst.copy_(src, non_blocking=True)
             (g1, g2, g3), out = self._graphs[with_r1]
             g1.replay()
@@ -110,7 +146,7 @@ class GifTrainer:
         state = {}
         self._seg1(state, real_image, flm_rndr, input_indices, with_r1)
         self.d_reducer.all_reduce_mean()
-        self._seg2(state, real_image, flm_rndr, input_indices, with_r1)
+        self._seg2(state, real_image, flm_rndr, input_indices, with_r1, *extra)
         self.g_reducer.all_reduce_mean()
         self._seg3(state, real_image, flm_rndr, input_indices, with_r1)
         return state["d_loss"], state["g_loss"]
@@ -134,7 +170,7 @@ class GifTrainer:
         d_loss.backward()
         st.update(w=w, fake=fake, d_loss=d_loss.detach())
 
-    def _seg2(self, st, real_image, flm_rndr, input_indices, with_r1):
+    def _seg2(self, st, real_image, flm_rndr, input_indices, with_r1, flm_lbls=None):
         G, D, step = self.generator, self.discriminator, self.step_idx
         self.d_optimizer.step()
         # ------------------------------------------------ G step (train.py:181-252)
@@ -144,6 +180,12 @@ class GifTrainer:
         g_loss = F.softplus(-predict).mean()
         if self.ppl is not None:                                                  # train.py:205-208, weight 2
             g_loss = g_loss + 2 * self.ppl.path_length_from(st["fake"], st["w"])
+        if self.interp_tex_loss is not None:                                      # train.py:224-238
+            u = torch.rand((), device=flm_lbls.device)                            # np.random.uniform(0, 1) there; device RNG here
+            flm_intrp = flm_lbls[:-1, :159] + u * (flm_lbls[1:, :159] - flm_lbls[:-1, :159])
+            g_loss = g_loss + self.interp_tex_loss.tex_sp_intrp_loss(
+                flm_intrp, G, step=step, alpha=1, max_ids=self.vocab, normal_maps_as_cond=True,
+                use_posed_constant_input=False, rendered_flame_as_condition=True)
         g_loss.backward()
         st["g_loss"] = g_loss.detach()
         st.pop("fake")

@@ -56,3 +56,31 @@ def test_eager_and_graph_iterations_agree(cuda, ppl):
     assert not torch.equal(t_g.g_running.state_dict()[k_used], p0[k_used])
     assert all(torch.isfinite(p).all() for p in t_g.discriminator.parameters())
     assert all(torch.isfinite(p).all() for p in t_g.generator.parameters())
+
+
+def test_texture_interpolation_loss_in_the_iteration(cuda):
+    """texture_loss=batch: the G step adds InterpolatedTextureLoss (train.py:224-238) on interpolated FLAME labels -- FLAME
+    decode, condition render, a second generator forward, texture stealing, pairwise loss -- eagerly and from CUDA graphs."""
+    from gif_b200 import ops
+    from gif_b200.train_step import GifTrainer
+    ops.set_precision("tf32")
+    res, b = 32, 4
+    tr = GifTrainer(cuda, res, vocab=16, r1_every=2, ppl=False, seed=5, texture_loss=b)
+    ref = GifTrainer(cuda, res, vocab=16, r1_every=2, ppl=False, seed=5)
+    g = torch.Generator().manual_seed(2)
+    flm = torch.cat([torch.randn(b, 150, generator=g), (torch.rand(b, 6, generator=g) * 2 - 1) * 0.3,
+                     torch.rand(b, 1, generator=g) * 3 + 7, (torch.rand(b, 2, generator=g) * 2 - 1) * 0.02], 1).to(cuda)
+    outs = []
+    for it in range(2):
+        real, cond, idx = _batch(10 * it, b, res, cuda)
+        d0, g0 = (float(v) for v in ref.train_iteration(real, cond, idx))
+        d1, g1 = (float(v) for v in tr.train_iteration(real, cond, idx, flm))
+        outs.append((d0, g0, d1, g1))
+    # iteration 0: identical weights -> identical D loss; the texture term is positive (>= 16 * 0.5 * masked-out fraction)
+    assert outs[0][0] == pytest.approx(outs[0][2], rel=2e-4)
+    assert outs[0][3] > outs[0][1] + 1.0
+    tr.capture(b, res)
+    for it in range(2, 5):
+        d1, g1 = (float(v) for v in tr.train_iteration(*_batch(10 * it, b, res, cuda), flm))
+        assert d1 == d1 and g1 == g1 and 0 < g1 < 1e3
+    assert all(torch.isfinite(p).all() for p in tr.generator.parameters())
