@@ -13,7 +13,6 @@ import math
 
 import torch
 
-from . import _lib
 from ._lib import check, lib, ptr, require_cuda, stream
 
 S1, S2, T2 = 0, 1, 2          # conv modes of gifb200_conv2d

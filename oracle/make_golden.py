@@ -5,7 +5,6 @@ the restatement in ``oracle/stylegan2_oracle.py`` against them (asserts, fp32 an
 Run in the build container only:   python -m oracle.make_golden
 The fixtures it writes are committed; the GPU box never needs /root/reference.
 """
-import math
 import os
 import sys
 

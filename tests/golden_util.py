@@ -8,7 +8,6 @@
   networks are numerically well-conditioned.
 * ``sample``: a fixed pseudo-random subsample of a tensor (goldens store samples + a float64 sum, not MBs).
 """
-import math
 import os
 
 import numpy as np

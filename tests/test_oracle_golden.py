@@ -1,8 +1,6 @@
 """CPU: the oracle restatement (oracle/stylegan2_oracle.py) against the golden vectors produced by the unmodified
 reference modules (oracle/make_golden.py).  Runs everywhere (no GPU, no /root/reference)."""
-import math
 
-import numpy as np
 import torch
 
 import golden_util as gu

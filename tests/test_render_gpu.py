@@ -1,6 +1,5 @@
 """GPU: the fused conditioning render (gif_b200.render.FlameRenderer: rasterise -> gifb200_render_shade) against the
 oracle (C rasteriser oracle + oracle/render_oracle.py) on the synthetic FLAME workload."""
-import numpy as np
 import pytest
 import torch
 
