@@ -393,7 +393,7 @@ def main():
                 "launches": len(prof), "kernel_ms_per_step": tot_ms / prof_steps,
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note}
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N=1 measurement
         cb = cpu_arm(1, 0)
     line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
