@@ -127,7 +127,7 @@ def usable_cores():
     return max(1, min(n, 32))
 
 
-def cpu_arm(steps, warmup):
+def cpu_arm(steps, warmup, budget_s=None):
     """The oracle port on the host cores: one D+G iteration at batch 1, 256^2 (no R1 / PPL) per step."""
     import golden_util as gu
     from oracle import stylegan2_oracle as O
@@ -153,14 +153,21 @@ def cpu_arm(steps, warmup):
         gl = O.g_nonsat_loss(O.discriminator_forward(fake, cond, sdd, RES))
         torch.autograd.grad(gl, [sdg[k] for k in gp], allow_unused=True)
 
+    t_all = time.perf_counter()
     for _ in range(warmup):
         one()
+        if budget_s is not None and time.perf_counter() - t_all > budget_s / 4:
+            break                                  # bounded: never spend more than a quarter of the budget warming up
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         one()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": b / dt, "unit": "images/sec", "cores": cores, "kind": "port",
-            "sample": f"{steps} iteration(s) of the D+G step at batch {b}, 256x256, no R1/PPL, oracle/stylegan2_oracle.py "
+        done += 1
+        if budget_s is not None and time.perf_counter() - t_all > budget_s:
+            break                                  # bounded sample: the run must end within minutes whatever K is
+    dt = (time.perf_counter() - t0) / max(done, 1)
+    return {"value": b / dt, "unit": "images/sec", "cores": cores, "kind": "port", "steps_done": done,
+            "sample": f"{done} iteration(s) of the D+G step at batch {b}, 256x256, no R1/PPL, oracle/stylegan2_oracle.py "
                       f"(torch CPU fp32, {cores} threads), {dt:.1f} s per iteration"}
 
 
@@ -168,10 +175,10 @@ def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 2))
-    cb = cpu_arm(steps, 1 if args.warmup > 0 else 0)
+    # K steps / W warm-ups as asked, each step a bounded sample (one batch-1 iteration), the whole run capped at ~3 minutes
+    cb = cpu_arm(max(1, args.steps), max(0, args.warmup), budget_s=180.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": 1000.0 / cb["value"],
+            "steps": cb["steps_done"], "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "train_step_256_bs32 (CPU arm: bounded sample at batch 1, see cpu_baseline.sample)"},
             "cpu_baseline": cb,
@@ -394,7 +401,7 @@ def main():
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note}
     cb = None
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N=1 measurement
-        cb = cpu_arm(1, 0)
+        cb = cpu_arm(3, 1, budget_s=40.0)             # ~10-30 s of CPU work on the box's host cores
     line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32 tensor-core contraction, f32 accumulate/storage", "data": "synthetic",
