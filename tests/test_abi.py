@@ -108,3 +108,26 @@ def test_install_as_reference_modules():
     import model.stg2_generator as g
     import model.stylegan2_common_layers as cl
     assert hasattr(g, "StyledGenerator") and hasattr(cl, "ModulatedConv2d") and hasattr(cl, "upfirdn2d")
+
+
+def test_discriminator_construction_and_minibatch_stddev_glue():
+    """CPU-checkable parts of the discriminator module: layer widths / key layout for every size, and the minibatch
+    standard-deviation feature against the oracle's restatement of disc.py:59-65."""
+    import torch
+    from gif_b200.model.stg2_discriminator import Discriminator, _channel_table, minibatch_stddev_feature
+    from oracle import stylegan2_oracle as O
+    assert _channel_table(2) == {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32}
+    assert _channel_table(1)[64] == 256 and _channel_table(1)[1024] == 16
+    for size, nblocks in ((4, 0), (16, 2), (256, 6), (1024, 8)):
+        D = Discriminator(size, num_color_chnls=9)
+        assert len(D.convs) == 1 + nblocks
+        assert D.convs[0][0].weight.shape == (_channel_table(2)[size], 9, 1, 1)
+        assert D.final_conv[0].weight.shape == (512, 513, 3, 3) and D.final_linear[0].weight.shape == (512, 8192)
+    g = torch.Generator().manual_seed(0)
+    for b in (1, 3, 4, 8, 32):
+        x = torch.randn(b, 512, 4, 4, generator=g, dtype=torch.float64)
+        if b % min(b, 4) != 0:
+            continue
+        y = minibatch_stddev_feature(x)
+        assert y.shape == (b, 513, 4, 4) and torch.equal(y[:, :512], x)
+        assert (y - O.minibatch_stddev(x, 4)).abs().max() < 1e-14
