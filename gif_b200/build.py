@@ -30,7 +30,20 @@ def _stamp(path):
 
 
 def build(verbose=False, force=False):
+    """Incremental (content-hash stamps).  Safe under ``torchrun``: an exclusive file lock serialises concurrent builders
+    (all ranks import the package at once), and every object / the library is written to a temporary name and renamed into
+    place, so a process that is not building never sees a half-written file."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose, force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose, force):
     objs, rebuilt = [], False
     for src in SOURCES:
         path = os.path.join(CSRC, src)
@@ -38,23 +51,28 @@ def build(verbose=False, force=False):
         stamp_file = obj + ".stamp"
         stamp = _stamp(path)
         if force or not os.path.isfile(obj) or not os.path.isfile(stamp_file) or open(stamp_file).read() != stamp:
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            tmp = obj + f".tmp{os.getpid()}"
+            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", tmp]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
                 raise RuntimeError(f"nvcc failed on {src}")
             if verbose:
                 print(r.stderr)
-            with open(stamp_file, "w") as f:
+            os.replace(tmp, obj)
+            with open(stamp_file + ".tmp", "w") as f:
                 f.write(stamp)
+            os.replace(stamp_file + ".tmp", stamp_file)
             rebuilt = True
         objs.append(obj)
     if rebuilt or not os.path.isfile(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        tmp = LIB + f".tmp{os.getpid()}"
+        cmd = [NVCC, "-shared", "-o", tmp] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.replace(tmp, LIB)
     return LIB
 
 

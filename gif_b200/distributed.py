@@ -35,9 +35,16 @@ def init_from_env(backend=None):
 
 
 class FlatGradAllReducer:
-    """Gradient exchange for one network: a flat fp32 buffer with one slot per parameter that can receive a gradient."""
+    """Gradient exchange for one network: a flat fp32 buffer with one slot per parameter that can receive a gradient.
 
-    def __init__(self, params, world_size=None, group=None):
+    ``attach()`` (called once, and again by ``zero()`` only if autograd replaced a ``.grad``) makes every parameter's
+    ``.grad`` a view into the flat buffer, so backward accumulates straight into it and the exchange is ONE collective
+    with no gather pass.  ``pre_scale()`` returns the 1/world factor to fold into the loss (so that the SUM all-reduce
+    already yields the mean and no separate scaling pass runs); ``all_reduce_mean()`` keeps the classic "sum then scale"
+    semantics for callers that did not pre-scale.  ``bucket_bytes`` splits the buffer into a few contiguous chunks issued
+    back to back as asynchronous collectives (they pipeline inside NCCL; the last one is waited on)."""
+
+    def __init__(self, params, world_size=None, group=None, bucket_bytes=None):
         self.params = [p for p in params]
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
@@ -50,28 +57,120 @@ class FlatGradAllReducer:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
         self.nbytes = n * 4
+        per = n if not bucket_bytes else max(1, int(bucket_bytes) // 4)
+        self.buckets = [self.flat[a:min(a + per, n)] for a in range(0, max(n, 1), per)] if n else []
+        self._attached = False
 
     def attach(self):
         """Make every parameter's .grad a view into the flat buffer (so backward accumulates straight into it)."""
-        self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v
+        self._attached = True
+
+    def _reattach_strays(self):
+        """Parameters whose .grad was replaced (autograd assigns a fresh tensor when .grad was None; optimizer.zero_grad
+        sets None): copy what they hold into the slot and point them back at it.  A no-op walk of pointer compares on the
+        steady-state path (nothing strays once attached)."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
 
     def zero(self):
         self.flat.zero_()
-        for p, v in zip(self.params, self.views):   # parameters unused in this step keep a zero gradient
-            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                p.grad = v
+        if not self._attached:
+            self.attach()
+        else:
+            for p, v in zip(self.params, self.views):      # parameters unused in this step keep a zero gradient
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v
+
+    def pre_scale(self):
+        """Factor to multiply the local loss by so that ``all_reduce_sum()`` leaves the MEAN gradient in the buffer."""
+        return 1.0 / self.world
+
+    def all_reduce_sum(self):
+        """SUM over ranks, in place, bucketed.  Use with a loss pre-scaled by ``pre_scale()``."""
+        self._reattach_strays()
+        if self.world > 1:
+            works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+            for w in works:
+                w.wait()
 
     def all_reduce_mean(self):
-        """SUM over ranks then 1/world.  Parameters whose .grad was replaced by autograd are copied back first."""
-        for p, v in zip(self.params, self.views):
-            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
-                p.grad = v
+        """SUM over ranks then 1/world (for losses that were not pre-scaled)."""
+        self.all_reduce_sum()
         if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
+
+
+class DataParallel(torch.nn.Module):
+    """Stand-in for ``torch.nn.DataParallel`` in the reference's train.py (:344, :356, :358, :367): exposes ``.module``
+    (so ``generator.module.get_embddings()``, ``generator.module.parameters()``, ``generator.module.z_to_w`` and the
+    ``module.``-prefixed checkpoint keys keep working), runs ``forward`` on the LOCAL replica only -- one process per GPU
+    replaces the reference's one-process scatter/replicate/gather -- and leaves the gradient exchange to the optimiser
+    hook below.  ``device_ids`` / ``output_device`` / ``dim`` are accepted and ignored."""
+
+    def __init__(self, module, device_ids=None, output_device=None, dim=0):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+
+_reducers = {}
+_hook_handle = None
+
+
+def _optimizer_pre_step_hook(optimizer, args, kwargs):
+    """Runs before EVERY ``optimizer.step()`` of the process once installed: averages the gradients of that optimiser's
+    parameters across ranks through a cached FlatGradAllReducer (train.py calls ``loss.backward(); optimizer.step()`` and
+    knows nothing about ranks).  Parameters without a gradient contribute zeros on this rank (another rank may have used
+    them)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    red = _reducers.get(id(optimizer))
+    params = [p for g in optimizer.param_groups for p in g["params"]]
+    if red is None or len(red.params) != len(params) or any(a is not b for a, b in zip(red.params, params)):
+        red = FlatGradAllReducer(params, dist.get_world_size())
+        _reducers[id(optimizer)] = red
+    for p, v in zip(params, red.views):
+        if p.grad is None:                     # e.g. the unused high-resolution blocks (gen.py:175): zeros from this rank.
+            v.zero_()                          # Adam's update for an all-zero gradient is exactly 0 (0 / (0 + eps))
+    red.all_reduce_mean()                      # strays are copied into their slots first
+    return None
+
+
+def install_data_parallel_shim():
+    """``torch.nn.DataParallel = gif_b200.distributed.DataParallel`` + the global optimiser pre-step hook.  Called by
+    ``gif_b200.install_as_reference_modules()`` so that the reference's train.py runs unchanged under
+    ``torchrun --nproc-per-node N train.py ...`` (one process per GPU, NCCL all-reduce instead of DataParallel's
+    scatter/gather).  Idempotent.  Returns the original class so a caller can restore it."""
+    global _hook_handle
+    original = getattr(torch.nn, "_gifb200_original_DataParallel", None) or torch.nn.DataParallel
+    torch.nn._gifb200_original_DataParallel = original
+    torch.nn.DataParallel = DataParallel
+    torch.nn.parallel.DataParallel = DataParallel
+    if _hook_handle is None:
+        from torch.optim.optimizer import register_optimizer_step_pre_hook
+        _hook_handle = register_optimizer_step_pre_hook(_optimizer_pre_step_hook)
+    return original
+
+
+def uninstall_data_parallel_shim():
+    global _hook_handle
+    original = getattr(torch.nn, "_gifb200_original_DataParallel", None)
+    if original is not None:
+        torch.nn.DataParallel = original
+        torch.nn.parallel.DataParallel = original
+    if _hook_handle is not None:
+        _hook_handle.remove()
+        _hook_handle = None
+    _reducers.clear()
 
 
 def broadcast_module(module, src=0):

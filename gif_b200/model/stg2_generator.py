@@ -2,8 +2,8 @@
 z->w mapping -> StyleGAN2 synthesis blocks at 4..256 (1024) with the 6-channel FLAME render injected as the
 "noise" input of every StyledConv.  Same class names, constructor / forward signatures and state_dict keys.
 
-(``FlameTextureSpace`` -- the texture-stealing helper of the interpolation loss, gen.py:336-421 -- is outside the
-hot path and is not provided.)
+``FlameTextureSpace`` (gen.py:336-421, imported from here by loss_functions/losses.py:9) is re-exported from
+``gif_b200.texture_space`` at the bottom of this file.
 """
 import random
 
@@ -181,3 +181,8 @@ class StyledGenerator(nn.Module):
         if mean_style is not None:
             styles = [mean_style + style_weight * (style - mean_style) for style in styles]
         return self.generator(styles, pose, noise, step, alpha, input_indices=input_indices, mixing_range=mixing_range)
+
+
+# loss_functions/losses.py:9 does ``from model.stg2_generator import FlameTextureSpace`` (class at gen.py:336); the
+# implementation (fused texture-stealing kernel + adjoint) lives in gif_b200/texture_space.py.
+from ..texture_space import FlameTextureSpace  # noqa: E402,F401

@@ -11,6 +11,7 @@ the tensor cores, and the demodulation coefficient d[b,o] scales the *output* (S
 reference to fp32 rounding).
 """
 import math
+import random
 
 import torch
 from torch import nn
@@ -384,6 +385,86 @@ def get_w_frm_z(n_mlp, style_dim, lr_mlp=1, scale_weight=1.0):
             return args[0]
 
     return Net()
+
+
+class Generator(nn.Module):
+    """cl.py:536-750: the plain StyleGAN2 synthesis stack (constant input, StyledConv pairs with single-channel noise inputs,
+    ToRGB skips).  Not used by GIF's training path (train.py builds ``model.stg2_generator.StyledGenerator``), and the
+    reference's own constructor cannot run (cl.py:569-571 passes ``style_dim`` positionally into StyledConv's
+    ``noise_in_dims`` slot AND ``noise_in_dims=1`` by keyword: TypeError), so its outputs are unpinned; this follows the
+    evident intent so that everything the reference's operator module exports is importable and runnable from this one.  Same attribute / state_dict
+    names (``style``, ``input``, ``conv1``, ``to_rgb1``, ``convs``, ``to_rgbs``, ``noises.noise_{i}``)."""
+
+    def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01):
+        super().__init__()
+        self.size = size
+        self.style_dim = style_dim
+        self.style = get_w_frm_z(n_mlp, style_dim, lr_mlp)
+        m = channel_multiplier
+        self.channels = {4: 512, 8: 512, 16: 512, 32: 512, 64: 256 * m, 128: 128 * m, 256: 64 * m, 512: 32 * m, 1024: 16 * m}
+        self.log_size = int(math.log(size, 2))
+        self.num_layers = (self.log_size - 2) * 2 + 1
+        self.n_latent = self.log_size * 2 - 2
+        width = self.channels[4]
+        self.input = ConstantInput(width)
+        self.conv1 = StyledConv(width, width, 3, style_dim=style_dim, blur_kernel=blur_kernel, noise_in_dims=1)
+        self.to_rgb1 = ToRGB(width, style_dim, upsample=False)
+        self.convs, self.upsamples, self.to_rgbs, self.noises = nn.ModuleList(), nn.ModuleList(), nn.ModuleList(), nn.Module()
+        for layer in range(self.num_layers):
+            r = 2 ** ((layer + 5) // 2)
+            self.noises.register_buffer(f'noise_{layer}', torch.randn(1, 1, r, r))
+        for octave in range(3, self.log_size + 1):
+            nxt = self.channels[2 ** octave]
+            self.convs.append(StyledConv(width, nxt, 3, style_dim=style_dim, upsample=True, blur_kernel=blur_kernel,
+                                         noise_in_dims=1))
+            self.convs.append(StyledConv(nxt, nxt, 3, style_dim=style_dim, blur_kernel=blur_kernel, noise_in_dims=1))
+            self.to_rgbs.append(ToRGB(nxt, style_dim))
+            width = nxt
+
+    def make_noise(self):
+        dev = self.input.input.device
+        sizes = [4] + [2 ** o for o in range(3, self.log_size + 1) for _ in range(2)]
+        return [torch.randn(1, 1, r, r, device=dev) for r in sizes]
+
+    def mean_latent(self, n_latent):
+        return self.style(torch.randn(n_latent, self.style_dim, device=self.input.input.device)).mean(0, keepdim=True)
+
+    def get_latent(self, input):
+        return self.style(input)
+
+    def _latents(self, styles, inject_index):
+        """cl.py:690-708: one w per layer; two styles are crossed over at ``inject_index``."""
+        if len(styles) < 2:
+            return styles[0].unsqueeze(1).repeat(1, self.n_latent, 1) if styles[0].ndim < 3 else styles[0]
+        if inject_index is None:
+            inject_index = random.randint(1, self.n_latent - 1)
+        return torch.cat([styles[0].unsqueeze(1).repeat(1, inject_index, 1),
+                          styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
+
+    def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
+                input_is_latent=False, noise=None, randomize_noise=True):
+        if not input_is_latent:
+            styles = [self.style(s) for s in styles]
+        if noise is None:
+            noise = [None] * self.num_layers if randomize_noise else \
+                [getattr(self.noises, f'noise_{i}') for i in range(self.num_layers)]
+        if truncation < 1:
+            styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+        latent = self._latents(styles, inject_index)
+        batch = latent.shape[0]
+
+        def per_sample(n):          # stored noises are (1,1,r,r): one map shared by the batch
+            return None if n is None else ops.to_nhwc(n.expand(batch, -1, -1, -1))
+        x = ops.to_nhwc(self.input(latent))
+        x = self.conv1.forward_nhwc(x, latent[:, 0], per_sample(noise[0]))
+        skip = self.to_rgb1.forward_nhwc(x, latent[:, 1], None)
+        for j, to_rgb in enumerate(self.to_rgbs):
+            i = 1 + 2 * j
+            x = self.convs[2 * j].forward_nhwc(x, latent[:, i], per_sample(noise[i]))
+            x = self.convs[2 * j + 1].forward_nhwc(x, latent[:, i + 1], per_sample(noise[i + 1]))
+            skip = to_rgb.forward_nhwc(x, latent[:, i + 2], skip)
+        image = ops.to_nchw_view(skip)
+        return (image, latent) if return_latents else (image, None)
 
 
 class ConvLayer(nn.Sequential):

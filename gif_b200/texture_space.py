@@ -83,12 +83,25 @@ class FlameTextureSpace(nn.Module):
     def __init__(self, texture_data, data_un_normalizer=None, flame=None, size=256):
         super().__init__()
         if flame is None:
-            raise ValueError("FlameTextureSpace needs a gif_b200.flame.FLAME decoder (flame=...)")
+            flame = self._flame_from_constants()
         self.texture_data = texture_data
         self.data_un_normalizer = data_un_normalizer
         self.flame = flame
         self.size = size
         self._table = None
+
+    @staticmethod
+    def _flame_from_constants():
+        """The reference builds its decoder from ``constants.flame_config`` (gen.py:343-347 via gif_helper.render_utils);
+        as a drop-in under the reference's tree the same config (and its licence-gated generic_model.pkl) is used."""
+        import types
+        try:
+            import constants as cnst
+        except ImportError as e:
+            raise ValueError("FlameTextureSpace needs a gif_b200.flame.FLAME decoder (flame=...) when the reference's "
+                             "`constants` module is not importable") from e
+        from .flame import FLAME
+        return FLAME(types.SimpleNamespace(**cnst.flame_config))
 
     def _tab(self, device):
         if self._table is None or self._table["vid"].device != device:
@@ -162,7 +175,7 @@ class InterpolatedTextureLoss:
                 m = torch.nn.functional.interpolate(m, size=textures.shape[-2:], mode="bilinear", align_corners=False)
                 self.face_region_only_mask = m
             per_pair = (torch.sigmoid(torch.pow(textures[i] * common - textures[j] * common, 2)) * m[0]).mean(dim=(1, 2, 3))
-            return 16 * per_pair.sum() / self.max_num
+            return 16 * per_pair.sum() / sel.numel()          # len(random_pairs), losses.py:176
         sel = self.rng.choice(len(self.pairs), self.max_num, replace=False)
         loss = 0
         for i, j in self.pairs[sel]:
@@ -173,6 +186,11 @@ class InterpolatedTextureLoss:
     def get_image_and_textures(self, alpha, flame_batch, generator, max_ids, normal_maps_as_cond,
                                rendered_flame_as_condition, step, use_posed_constant_input):
         """losses.py:178-235: one identity for the whole (truncated) batch, one generator forward, texture stealing."""
+        if flame_batch.shape[0] < self.max_num:
+            # the pair table indexes textures 0..max_num-1 (losses.py:141-145); a shorter batch would be an out-of-range
+            # device gather (an assert that poisons the context, or garbage under graph replay), not an IndexError
+            raise ValueError(f"InterpolatedTextureLoss(max_images_in_batch={self.max_num + 1}) needs at least {self.max_num} "
+                             f"interpolated label rows, got {flame_batch.shape[0]}: build it with the per-GPU batch size")
         flame_batch = flame_batch[:self.max_num, :]
         with torch.no_grad():
             cond = self.render_condition(flame_batch)

@@ -23,6 +23,10 @@ from .model.stg2_discriminator import Discriminator
 from .model.stg2_generator import StyledGenerator
 
 
+def world_gt1(reducer):
+    return reducer.world > 1
+
+
 def requires_grad(model, flag=True):
     """my_utils/generic_utils.py:58-60."""
     for p in model.parameters():
@@ -39,7 +43,7 @@ def accumulate(model1, model2, decay=0.999):
 
 class GifTrainer:
     def __init__(self, device, resolution=256, vocab=70_000, r1_every=16, ppl=False, world_size=1, seed=0,
-                 texture_loss=False):
+                 texture_loss=False, embedding_reg_weight=0.0, adaptive_interp_loss=False):
         torch.manual_seed(seed)
         self.device = device
         self.step_idx = int(math.log2(resolution)) - 2                           # train.py:387
@@ -56,6 +60,8 @@ class GifTrainer:
         self.g_reducer = FlatGradAllReducer(list(self.generator.parameters()), world_size)
         self.d_reducer = FlatGradAllReducer(list(self.discriminator.parameters()), world_size)
         self.r1_every = r1_every
+        self.embedding_reg_weight = float(embedding_reg_weight)      # train.py:216-219 (0 in every shipped configuration)
+        self.adaptive_interp_loss = bool(adaptive_interp_loss)       # train.py:236-237
         self.ppl = losses.PathLengthRegularizor() if ppl else None
         self.iteration = 0
         self._graphs = None
@@ -138,16 +144,16 @@ class GifTrainer:
                 dst.copy_(src, non_blocking=True)
             (g1, g2, g3), out = self._graphs[with_r1]
             g1.replay()
-            self.d_reducer.all_reduce_mean()
+            self.d_reducer.all_reduce_sum()
             g2.replay()
-            self.g_reducer.all_reduce_mean()
+            self.g_reducer.all_reduce_sum()
             g3.replay()
             return out
         state = {}
         self._seg1(state, real_image, flm_rndr, input_indices, with_r1)
-        self.d_reducer.all_reduce_mean()
+        self.d_reducer.all_reduce_sum()
         self._seg2(state, real_image, flm_rndr, input_indices, with_r1, *extra)
-        self.g_reducer.all_reduce_mean()
+        self.g_reducer.all_reduce_sum()
         self._seg3(state, real_image, flm_rndr, input_indices, with_r1)
         return state["d_loss"], state["g_loss"]
 
@@ -167,7 +173,8 @@ class GifTrainer:
             real_loss = real_loss + losses.grad_penalty_loss([real_image], real_scores, step=None).mean()
         fake_scores, _ = D([fake.detach()], condition=flm_rndr, step=step, alpha=1)   # train.py:160-170
         d_loss = real_loss + F.softplus(fake_scores).mean()
-        d_loss.backward()
+        # 1/world folded into the backward seed: the SUM all-reduce then leaves the mean gradient (no scaling pass)
+        (d_loss * self.d_reducer.pre_scale() if world_gt1(self.d_reducer) else d_loss).backward()
         st.update(w=w, fake=fake, d_loss=d_loss.detach())
 
     def _seg2(self, st, real_image, flm_rndr, input_indices, with_r1, flm_lbls=None):
@@ -180,13 +187,18 @@ class GifTrainer:
         g_loss = F.softplus(-predict).mean()
         if self.ppl is not None:                                                  # train.py:205-208, weight 2
             g_loss = g_loss + 2 * self.ppl.path_length_from(st["fake"], st["w"])
+        if self.embedding_reg_weight != 0.0:                                      # train.py:216-219
+            g_loss = g_loss + self.embedding_reg_weight * losses.l2_reg(G.z_to_w)
         if self.interp_tex_loss is not None:                                      # train.py:224-238
             u = torch.rand((), device=flm_lbls.device)                            # np.random.uniform(0, 1) there; device RNG here
             flm_intrp = flm_lbls[:-1, :159] + u * (flm_lbls[1:, :159] - flm_lbls[:-1, :159])
-            g_loss = g_loss + self.interp_tex_loss.tex_sp_intrp_loss(
+            interp = self.interp_tex_loss.tex_sp_intrp_loss(
                 flm_intrp, G, step=step, alpha=1, max_ids=self.vocab, normal_maps_as_cond=True,
                 use_posed_constant_input=False, rendered_flame_as_condition=True)
-        g_loss.backward()
+            if self.adaptive_interp_loss:                                         # train.py:236-237
+                interp = interp * (0.25 * g_loss.detach() / interp.detach())
+            g_loss = g_loss + interp
+        (g_loss * self.g_reducer.pre_scale() if world_gt1(self.g_reducer) else g_loss).backward()
         st["g_loss"] = g_loss.detach()
         st.pop("fake")
         st.pop("w")

@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE -- drives the reference's UNMODIFIED ``train()`` (train.py:28-312) on a synthetic dataset.
+
+Used three ways, always with the same seeded inputs and initial weights:
+  * ``oracle/make_train_golden.py`` (build container): train() over the reference's OWN model / loss modules on the CPU
+    -> ``tests/golden/train_loop.npz`` (parameters, EMA generator, Adam moments after 1 and after 16 iterations; the 16th
+    is the first R1 iteration, train.py:145);
+  * ``tests/test_dropin_train_gpu.py``: the same train() over THIS repo's drop-in modules
+    (``gif_b200.install_as_reference_modules()``: model.* and nn.DataParallel resolve here) -> must reproduce the golden:
+    the boundary test of SURVEY 8b and the loop-body parity of 8a L4 in one;
+  * the same test file runs ``gif_b200.train_step.GifTrainer`` (one shared G forward, flat gradient buffers, fused Adam)
+    on the same batches against the same golden.
+``train()`` reads four globals that train.py defines under ``__main__`` (g_optimizer, d_optimizer_flm, g_running,
+n_critic; train.py:322,365-382): ``run_reference_train`` sets them on the module exactly as ``__main__`` would.
+"""
+import contextlib
+import math
+import types
+
+import numpy as np
+import torch
+
+import golden_util as gu
+
+RES, BATCH, VOCAB, ITERS = 16, 4, 50, 16
+G_SEED, D_SEED, RUNNING_SEED = 11, 12, 13
+
+G_WATCH = ["generator.progression.0.st_cv1.conv.weight", "generator.progression.2.st_cv2.conv.weight",
+           "generator.progression.1.st_cv1.conv.modulation.weight", "generator.progression.2.st_cv1.noise.noise_conv.4.weight",
+           "generator.progression.2.st_cv2.activate.bias", "generator.to_rgb.2.conv.weight", "generator.to_rgb.1.bias",
+           "generator.const_input.input", "z_to_w.1.weight", "z_to_w.8.bias"]
+D_WATCH = ["convs.0.0.weight", "convs.0.1.bias", "convs.1.conv1.0.weight", "convs.1.conv2.1.weight", "convs.2.skip.1.weight",
+           "convs.2.conv2.2.bias", "final_conv.0.weight", "final_linear.0.weight", "final_linear.1.weight", "final_linear.1.bias"]
+
+
+class StopTraining(Exception):
+    pass
+
+
+def batch(i, device="cpu"):
+    """Iteration i's batch: FFHQ-shaped image in [-1,1], 6-channel condition in [-1,1], FLAME labels, identity indices."""
+    real = gu.rand_uniform((BATCH, 3, RES, RES), 7000 + 4 * i)
+    cond = gu.rand_uniform((BATCH, 6, RES, RES), 7001 + 4 * i)
+    lbls = gu.randn((BATCH, 159), 7002 + 4 * i)
+    idx = gu.randint(VOCAB, (BATCH,), 7003 + 4 * i)
+    return real.to(device), cond.to(device), lbls.to(device), idx.to(device)
+
+
+class SyntheticDataset:
+    """What train() touches of the dataset object (train.py:120-122, :230, :269)."""
+
+    def __init__(self, on_iteration_start=None):
+        self.calls = 0
+        self.on_iteration_start = on_iteration_start
+
+    def accumulate_batches_of_flm(self, flm, pose):     # called once per iteration, after the batch was drawn
+        if self.on_iteration_start is not None:
+            self.on_iteration_start(self.calls)          # == number of COMPLETED iterations
+        self.calls += 1
+
+    def un_normalize_flame(self, x):
+        return x
+
+
+def make_args():
+    return types.SimpleNamespace(
+        embedding_vocab_size=VOCAB, gen_reg_type="None", batch={RES: BATCH}, batch_default=BATCH, debug=True,
+        lr={}, use_styled_conv_stylegan2=True, max_size=RES, init_size=RES, phase=10 ** 9, ckpt=None,
+        rendered_flame_as_condition=True, normal_maps_as_cond=True, shfld_cond_as_neg_smpl=False, embedding_reg_weight=0.0,
+        apply_texture_space_interpolation_loss=False, adaptive_interp_loss=False, use_posed_constant_input=False, run_id="t")
+
+
+def _loader(n_iters):
+    def sample_data(dataset, batch_size, image_sizes, debug=False):
+        assert batch_size == BATCH and image_sizes[-1] == RES
+
+        class Loader:
+            def __iter__(self):
+                def gen():
+                    for i in range(n_iters):
+                        real, cond, lbls, idx = batch(i)
+                        yield real, [cond], [lbls], idx
+                    raise StopTraining()
+                return gen()
+        return Loader()
+    return sample_data
+
+
+@contextlib.contextmanager
+def cuda_calls_are_noops_without_a_gpu():
+    """train() calls ``.cuda()`` on its batches (train.py:125-130); in the GPU-less build container those become no-ops so
+    that the unmodified function runs on the CPU."""
+    if torch.cuda.is_available():
+        yield
+        return
+    t_cuda, m_cuda = torch.Tensor.cuda, torch.nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = t_cuda, m_cuda
+
+
+def initial_state_dicts():
+    g = gu.seeded_state_dict(gu.g_shapes(VOCAB), G_SEED)
+    d = gu.seeded_state_dict(gu.d_shapes(RES), D_SEED)
+    r = gu.seeded_state_dict(gu.g_shapes(VOCAB), RUNNING_SEED)
+    r["image_embedding.embd_weight"] = r["img_embdng.embd_weight"] = g["image_embedding.embd_weight"]
+    return g, d, r
+
+
+def build_networks(gen_mod, disc_mod, device):
+    """StyledGenerator x2 + Discriminator from the given (reference or drop-in) modules, seeded weights."""
+    g_sd, d_sd, r_sd = initial_state_dicts()
+    kw = dict(embedding_vocab_size=VOCAB, rendered_flame_ascondition=True, normal_maps_as_cond=True, core_tensor_res=4, n_mlp=8)
+    with contextlib.redirect_stdout(None):
+        G, Gr = gen_mod.StyledGenerator(**kw), gen_mod.StyledGenerator(**kw)
+        D = disc_mod.Discriminator(size=RES, num_color_chnls=9, channel_multiplier=2)
+    G.load_state_dict(g_sd)
+    Gr.load_state_dict(r_sd)
+    D.load_state_dict(d_sd)
+    return G.to(device), D.to(device), Gr.to(device)
+
+
+def run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after=(1,)):
+    """Runs train_mod.train() for n_iters iterations.  Returns {k: snapshot} for k in snapshot_after + (n_iters,)."""
+    with cuda_calls_are_noops_without_a_gpu():
+        return _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after)
+
+
+def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after):
+    from torch import nn, optim
+    generator = nn.DataParallel(G).cuda()                  # train.py:344 (the drop-in's stand-in when it is installed)
+    discriminator = nn.DataParallel(D).cuda()              # train.py:356
+    g_running = nn.DataParallel(Gr).cuda()                 # train.py:358
+    g_running.train(False)
+    g_ratio, d_ratio = 4 / 5, 16 / 17                      # train.py:365-382
+    train_mod.g_optimizer = optim.Adam(generator.module.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+    train_mod.d_optimizer_flm = optim.Adam(discriminator.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
+    train_mod.g_running = g_running
+    train_mod.n_critic = 1                                 # train.py:322
+    train_mod.sample_data = _loader(n_iters)
+    snaps = {}
+
+    def snap(done):
+        if done in snapshot_after or done == n_iters:
+            snaps[done] = snapshot(generator.module, discriminator.module, g_running.module,
+                                   train_mod.g_optimizer, train_mod.d_optimizer_flm)
+
+    class Bar:                                             # ``pbar = tqdm(range(...))`` then ``pbar.set_description``
+        def __init__(self, it):
+            self.it = it
+
+        def __iter__(self):
+            return iter(self.it)
+
+        def set_description(self, *_a, **_k):
+            pass
+    train_mod.tqdm = Bar
+    dataset = SyntheticDataset(on_iteration_start=snap)
+    try:
+        train_mod.train(make_args(), dataset, generator, discriminator, None, None, 0, int(math.log2(RES)) - 2)
+    except StopTraining:
+        pass
+    snap(n_iters)
+    return snaps
+
+
+def snapshot(G, D, Gr, g_opt, d_opt):
+    """Sampled parameters / EMA parameters / Adam second moments as float64 numpy (+ norms)."""
+    out = {}
+    for tag, net, names in (("g", G, G_WATCH), ("d", D, D_WATCH), ("r", Gr, G_WATCH)):
+        named = dict(net.named_parameters())
+        for n in names:
+            s, tot = gu.sample(named[n], 1024, 5)
+            out[f"{tag}|{n}"] = s
+            out[f"{tag}|{n}|norm"] = np.array(float(named[n].detach().double().norm()))
+        flat = torch.cat([p.detach().reshape(-1).double().cpu() for p in net.parameters()])
+        out[f"{tag}|all"] = gu.sample(flat, 16384, 6)[0]
+        out[f"{tag}|all|norm"] = np.array(float(flat.norm()))
+    for tag, opt, net, names in (("g", g_opt, G, G_WATCH), ("d", d_opt, D, D_WATCH)):
+        named = dict(net.named_parameters())
+        for n in names:
+            st = opt.state.get(named[n])
+            if st:
+                out[f"{tag}|{n}|exp_avg_sq"] = gu.sample(st["exp_avg_sq"], 1024, 7)[0]
+    return out
+
+
+def flatten_snaps(snaps):
+    return {f"it{k}|{n}": v for k, s in snaps.items() for n, v in s.items()}
+
+
+def compare(snap, golden, it, tol_d, tol_g, tol_moment):
+    """L2-relative deviation of every watched tensor from the golden (parameters: relative to the parameter norm)."""
+    worst = {}
+    for key, got in snap.items():
+        if key.endswith("|norm"):
+            continue
+        ref = golden[f"it{it}|{key}"]
+        tag = key.split("|")[0]
+        if key.endswith("exp_avg_sq"):
+            err, tol = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300), tol_moment
+        else:
+            err, tol = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300), (tol_d if tag == "d" else tol_g)
+        worst[key] = (float(err), tol)
+    bad = {k: v for k, v in worst.items() if not v[0] < v[1]}
+    return worst, bad

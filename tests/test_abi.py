@@ -104,7 +104,7 @@ def test_no_cpu_fallback():
 
 def test_install_as_reference_modules():
     import gif_b200
-    gif_b200.install_as_reference_modules()
+    gif_b200.install_as_reference_modules(data_parallel=False)
     import model.stg2_generator as g
     import model.stylegan2_common_layers as cl
     assert hasattr(g, "StyledGenerator") and hasattr(cl, "ModulatedConv2d") and hasattr(cl, "upfirdn2d")

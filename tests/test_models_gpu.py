@@ -170,7 +170,7 @@ def test_path_length_regulariser_vs_oracle(cuda, fp32_mode):
 
 def test_drop_in_module_names():
     import gif_b200
-    gif_b200.install_as_reference_modules()
+    gif_b200.install_as_reference_modules(data_parallel=False)
     from model.stg2_generator import StyledGenerator  # noqa: F401
     from model.stg2_discriminator import Discriminator  # noqa: F401
     from model.stylegan2_common_layers import (Blur, ConvLayer, EqualConv2d, EqualLinear, FusedLeakyReLU,  # noqa: F401
