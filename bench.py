@@ -69,6 +69,8 @@ def parse():
     ap.add_argument("--texture-loss", action="store_true",
                     help="also time the step of the flagship reference run: no PPL, + texture-space interpolation loss")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16x3"],
+                    help="contraction mode of the tensor-core kernels (gif_b200.ops.set_precision)")
     return ap.parse_args()
 
 
@@ -206,7 +208,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    ops.set_precision("tf32")
+    ops.set_precision(args.precision)
     B = args.batch
     trainer = GifTrainer(dev, RES, VOCAB, r1_every=16, ppl=not args.no_ppl, world_size=world, seed=0)
     broadcast_module(trainer.generator)

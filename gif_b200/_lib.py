@@ -29,6 +29,7 @@ SIGNATURES = {
     "gifb200_conv2d_wgrad_workspace_bytes": (_sz, [_i] * 10),
     "gifb200_conv2d_wgrad_path": (_i, [_i] * 10),
     "gifb200_conv2d_wgrad": (_i, [_p, _p, _p] + [_i] * 12 + [_p, _sz, _p]),
+    "gifb200_split_bf16": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "gifb200_upfirdn2d": (_i, [_p, _p, _p] + [_i] * 14 + [_p]),
     "gifb200_bias_act": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p]),
     "gifb200_act_bwd": (_i, [_p, _p, _p, _ll, _f, _f, _i, _p]),

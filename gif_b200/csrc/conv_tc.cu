@@ -19,6 +19,14 @@
 // Operand precision: kind::tf32 reads the upper 19 bits of each fp32 (truncation).  Callers hand in activations that
 // are already rounded to tf32 (gif_b200.ops rounds in the producing kernel), weights are rounded here, so the
 // truncation is exact and the contraction is an unbiased tf32 x tf32 -> fp32 product sum.
+//
+// X3 = true is the error-compensated mode ("bf16x3", gifb200_conv2d impl 3): operands arrive as two bf16 planes (hi, lo)
+// per tensor (gifb200_split_bf16; the weights are split while staging), a stage holds the hi and the lo tile of A and of B
+// as K-major SWIZZLE_64B tiles of 32 channels (128 rows x 64 B: the SAME number of bytes per stage as the fp32 tiles), and
+// each 16-channel slice issues three kind::f16 MMAs -- lo*hi, hi*lo, hi*hi -- into the one fp32 TMEM accumulator.
+// Everything else (tile walk, ring, double-buffered TMEM, epilogue) is shared with the tf32 kernel.
+#include <cuda_bf16.h>
+
 #include "tc_common.cuh"
 
 namespace gifb200 {
@@ -81,9 +89,11 @@ __device__ __forceinline__ void decode_tile(int tile, int nblocks, int nphase, i
 // Persistent: gridDim.x CTAs (<= 2 per SM) walk the tile list (see decode_tile).
 // The smem ring and its phase bits run continuously across tiles; the TMEM accumulator is double buffered so the
 // epilogue of tile i overlaps the main loop of tile i+1 of the same CTA (and the second resident CTA fills the rest).
-template <int BLOCK_N>
+template <int BLOCK_N, bool X3>
 __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                         const __grid_constant__ CUtensorMap map_a2,
                                                          const __grid_constant__ CUtensorMap map_b,
+                                                         const __grid_constant__ CUtensorMap map_b2,
                                                          float* __restrict__ y, const TcParams p, const int mtiles,
                                                          const int total_tiles) {
     using L = SmemLayout<BLOCK_N>;
@@ -104,6 +114,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (X3) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b2) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -145,25 +159,35 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                 }
                 __syncwarp();
                 const int dy = p.tap_dy[phase][tap], dx = p.tap_dx[phase][tap];
+                // X3: the hi plane's tile fills the first half of the A (B) slot, the lo plane's tile the second half
                 if (!p.s2) {
-                    if (lane == 0) tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+                    if (lane == 0) {
+                        tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+                        if (X3) tma_load_4d(a_dst + kATileBytes / 2, &map_a2, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
+                    }
                 } else {
                     const int par = p.tap_par[phase][tap];
-                    const int row_bytes = p.wt * kBlockK * 4;
+                    const int row_bytes = p.wt * kBlockK * (X3 ? 2 : 4);
                     const int rows = p.nt * p.ht;
                     for (int r = lane; r < rows; r += 32) {
                         const int n = r / p.ht, h = r - n * p.ht;
                         tma_load_5d(a_dst + r * row_bytes, &map_a, &full_bar[stage], c0, par, x0 + dx,
                                     (y0 + h) * p.in_sy + dy, n0 + n);
+                        if (X3)
+                            tma_load_5d(a_dst + kATileBytes / 2 + r * row_bytes, &map_a2, &full_bar[stage], c0, par, x0 + dx,
+                                        (y0 + h) * p.in_sy + dy, n0 + n);
                     }
                 }
-                if (lane == 0) tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+                if (lane == 0) {
+                    tma_load_3d(b_dst, &map_b, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+                    if (X3) tma_load_3d(b_dst + L::kBTileBytes / 2, &map_b2, &full_bar[stage], c0, nblk * BLOCK_N, p.tap_w[phase][tap]);
+                }
                 if (++stage == kStages) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_tf32(kBlockM, BLOCK_N);
+        constexpr uint32_t idesc = X3 ? make_idesc_bf16(kBlockM, BLOCK_N) : make_idesc_tf32(kBlockM, BLOCK_N);
         int stage = 0;
         uint32_t ph = 0;
         int local = 0;
@@ -179,11 +203,25 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                 mbar_wait(&full_bar[stage], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-                const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-                const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
+                if (X3) {
+                    // v = hi + lo per operand: acc += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the 2^-18 lo*lo term is dropped);
+                    // small terms first.  UMMA_K = 16 bf16 = 32 bytes: two slices per 32-channel stage.
+                    const uint64_t ah = make_kmajor_sw64_desc(a_addr), al = make_kmajor_sw64_desc(a_addr + kATileBytes / 2);
+                    const uint64_t bh = make_kmajor_sw64_desc(a_addr + kATileBytes);
+                    const uint64_t bl = make_kmajor_sw64_desc(a_addr + kATileBytes + L::kBTileBytes / 2);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
-                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        umma_bf16(tmem_d, al + 2 * k, bh + 2 * k, idesc, (it | k) != 0);
+                        umma_bf16(tmem_d, ah + 2 * k, bl + 2 * k, idesc, 1);
+                        umma_bf16(tmem_d, ah + 2 * k, bh + 2 * k, idesc, 1);
+                    }
+                } else {
+                    const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                    const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
+                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                }
                 umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                 if (++stage == kStages) { stage = 0; ph ^= 1; }
             }
@@ -247,7 +285,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
     }
 }
 
-// stage logical weights W[t][o][i] (from the physical buffer + flip/transposed) as [T][Co][Ci], rounded to tf32
+// stage logical weights W[t][o][i] (from the physical buffer + flip/transposed) as [T][Co][Ci], rounded to tf32;
+// X3: as two bf16 planes [2][T][Co][Ci] (hi, lo) in the same number of bytes
+template <bool X3>
 __global__ void __launch_bounds__(256) stage_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int T,
                                                             int Co, int Ci, int flip, int transposed) {
     const long long total = static_cast<long long>(T) * Co * Ci;
@@ -259,7 +299,14 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const float* __restr
         const int tt = flip ? T - 1 - t : t;
         const float v = transposed ? w[(static_cast<long long>(tt) * Ci + i) * Co + o]
                                    : w[(static_cast<long long>(tt) * Co + o) * Ci + i];
-        out[e] = round_tf32(v);
+        if (X3) {
+            __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(out);
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            planes[e] = h;
+            planes[total + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+        } else {
+            out[e] = round_tf32(v);
+        }
     }
 }
 
@@ -275,17 +322,27 @@ int pick_block_n(int Co) {
 
 // T2 corner pixel (2*Hi, 2*Wi): only tap (2,2) on input pixel (Hi-1, Wi-1) reaches it.  One warp per (b, o), staged
 // (tf32-rounded) weights like the tensor-core path.
-__global__ void __launch_bounds__(256) t2_corner_kernel(const float* __restrict__ xpix, const float* __restrict__ w22,
+// X3: xpix / w22 point into the hi planes; the lo planes lie x_plane / w_plane elements further.
+template <bool X3>
+__global__ void __launch_bounds__(256) t2_corner_kernel(const void* __restrict__ xpix_v, const void* __restrict__ w22_v,
                                                         float* __restrict__ y, int B, long long x_batch_stride, int Ci, int Co,
-                                                        int Ho, int Wo, ConvEpilogue epi) {
+                                                        int Ho, int Wo, ConvEpilogue epi, long long x_plane, long long w_plane) {
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= static_cast<long long>(B) * Co) return;
     const int b = static_cast<int>(warp / Co), o = static_cast<int>(warp % Co);
-    const float* xv = xpix + b * x_batch_stride;
-    const float* wv = w22 + static_cast<long long>(o) * Ci;
     float a = 0.f;
-    for (int i = lane; i < Ci; i += 32) a = fmaf(xv[i], wv[i], a);
+    if (X3) {
+        const __nv_bfloat16* xv = static_cast<const __nv_bfloat16*>(xpix_v) + b * x_batch_stride;
+        const __nv_bfloat16* wv = static_cast<const __nv_bfloat16*>(w22_v) + static_cast<long long>(o) * Ci;
+        for (int i = lane; i < Ci; i += 32)
+            a = fmaf(__bfloat162float(xv[i]) + __bfloat162float(xv[x_plane + i]),
+                     __bfloat162float(wv[i]) + __bfloat162float(wv[w_plane + i]), a);
+    } else {
+        const float* xv = static_cast<const float*>(xpix_v) + b * x_batch_stride;
+        const float* wv = static_cast<const float*>(w22_v) + static_cast<long long>(o) * Ci;
+        for (int i = lane; i < Ci; i += 32) a = fmaf(xv[i], wv[i], a);
+    }
     a = warp_sum(a);
     if (lane == 0) y[((static_cast<long long>(b) * Ho + (Ho - 1)) * Wo + (Wo - 1)) * Co + o] = apply_epilogue(epi, a, o);
 }
@@ -294,21 +351,34 @@ void site_grid(int Hi, int Wi, int Ho, int Wo, int mode, int& Hs, int& Ws) {
     if (mode == 2) { Hs = Hi; Ws = Wi; } else { Hs = Ho; Ws = Wo; }
 }
 
-template <int BLOCK_N>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, float* y, const TcParams& p, int mtiles, cudaStream_t st) {
+template <int BLOCK_N, bool X3>
+int launch(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mb2, float* y,
+           const TcParams& p, int mtiles, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N>;
     static bool attr_set = false;   // per-process, idempotent
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(conv_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
     const long long total = static_cast<long long>(mtiles) * (p.Co / BLOCK_N) * p.nphase;
     if (total > 2147483647LL) return fail(GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
     const int grid = total < 2 * kNumSMs ? static_cast<int>(total) : 2 * kNumSMs;   // persistent: <= 2 CTAs per SM
-    conv_tc_kernel<BLOCK_N><<<grid, kTcThreads, L::kDynamic, st>>>(ma, mb, y, p, mtiles, static_cast<int>(total));
+    conv_tc_kernel<BLOCK_N, X3><<<grid, kTcThreads, L::kDynamic, st>>>(ma, ma2, mb, mb2, y, p, mtiles, static_cast<int>(total));
     GIFB200_LAUNCH_CHECK("conv_tc_kernel");
     return GIFB200_OK;
+}
+
+int launch_any(int bn, bool x3, const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mb2,
+               float* y, const TcParams& p, int mtiles, cudaStream_t st) {
+    if (x3) {
+        if (bn == 128) return launch<128, true>(ma, ma2, mb, mb2, y, p, mtiles, st);
+        if (bn == 64) return launch<64, true>(ma, ma2, mb, mb2, y, p, mtiles, st);
+        return launch<32, true>(ma, ma2, mb, mb2, y, p, mtiles, st);
+    }
+    if (bn == 128) return launch<128, false>(ma, ma2, mb, mb2, y, p, mtiles, st);
+    if (bn == 64) return launch<64, false>(ma, ma2, mb, mb2, y, p, mtiles, st);
+    return launch<32, false>(ma, ma2, mb, mb2, y, p, mtiles, st);
 }
 
 }  // namespace
@@ -330,7 +400,8 @@ size_t conv2d_tc_workspace_bytes(int, int, int, int Ci, int, int, int Co, int k,
 }
 
 int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
-              int mode, int flip, int transposed, const ConvEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st) {
+              int mode, int flip, int transposed, const ConvEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st,
+              bool x3) {
     GIFB200_REQUIRE(conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE, "conv2d_tc: unsupported shape");
     GIFB200_REQUIRE(ws && ws_bytes >= conv2d_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, transposed),
                     GIFB200_E_WORKSPACE, "conv2d_tc: workspace too small (see gifb200_conv2d_workspace_bytes)");
@@ -341,9 +412,18 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         const long long total = static_cast<long long>(T) * Co * Ci;
         int blocks = cdiv(total, 256 * 4);
         if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-        stage_weights_kernel<<<blocks, 256, 0, st>>>(w, wst, T, Co, Ci, flip, transposed);
+        if (x3) stage_weights_kernel<true><<<blocks, 256, 0, st>>>(w, wst, T, Co, Ci, flip, transposed);
+        else stage_weights_kernel<false><<<blocks, 256, 0, st>>>(w, wst, T, Co, Ci, flip, transposed);
         GIFB200_LAUNCH_CHECK("stage_weights_kernel");
     }
+    // element size / tile geometry of the operand tensors: fp32 + 128-byte swizzle rows, or bf16 planes + 64-byte rows
+    const cuuint64_t es = x3 ? 2 : 4;
+    const CUtensorMapSwizzle swz = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dt = x3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const long long x_plane = static_cast<long long>(B) * Hi * Wi * Ci;       // elements between the hi and the lo plane
+    const long long w_plane = static_cast<long long>(T) * Co * Ci;
+    const char* xb = reinterpret_cast<const char*>(x);
+    const char* wb = reinterpret_cast<const char*>(wst);
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.Ci = Ci; p.Co = Co; p.Ho = Ho; p.Wo = Wo; p.epi = epi;
@@ -384,35 +464,37 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         }
     }
     // ---- tensor maps
-    CUtensorMap ma, mb;
+    CUtensorMap ma, ma2, mb, mb2;
     int rc;
     if (mode != 1) {
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(Wi), static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Wi) * Ci * 4,
-                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * es, static_cast<cuuint64_t>(Wi) * Ci * es,
+                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * es};
         const cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(p.wt), static_cast<cuuint32_t>(p.ht), static_cast<cuuint32_t>(p.nt)};
-        rc = encode_map(&ma, x, 4, dims, strides, box);
+        rc = encode_map(&ma, xb, 4, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&ma2, xb + x_plane * es, 4, dims, strides, box, swz, dt);
     } else {
         // (C, parity, ceil(W/2), H, N): column 2*j + par of row h.  The (par=1, j=W/2) element of an odd-width row lies in
         // the next row; it is never addressed (max column read is 2*(Wo-1)+2 = Wi-1).
         const cuuint64_t dims[5] = {static_cast<cuuint64_t>(Ci), 2, static_cast<cuuint64_t>((Wi + 1) / 2), static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Ci) * 8,
-                                       static_cast<cuuint64_t>(Wi) * Ci * 4, static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(Ci) * es, static_cast<cuuint64_t>(Ci) * 2 * es,
+                                       static_cast<cuuint64_t>(Wi) * Ci * es, static_cast<cuuint64_t>(Hi) * Wi * Ci * es};
         const cuuint32_t box[5] = {kBlockK, 1, static_cast<cuuint32_t>(p.wt), 1, 1};
-        rc = encode_map(&ma, x, 5, dims, strides, box);
+        rc = encode_map(&ma, xb, 5, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&ma2, xb + x_plane * es, 5, dims, strides, box, swz, dt);
     }
     if (rc != GIFB200_OK) return rc;
     const int bn = pick_block_n(Co);
     {
         const cuuint64_t dims[3] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(Co), static_cast<cuuint64_t>(T)};
-        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Co) * Ci * 4};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(Ci) * es, static_cast<cuuint64_t>(Co) * Ci * es};
         const cuuint32_t box[3] = {kBlockK, static_cast<cuuint32_t>(bn), 1};
-        rc = encode_map(&mb, wst, 3, dims, strides, box);
+        rc = encode_map(&mb, wb, 3, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&mb2, wb + w_plane * es, 3, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
     }
-    if (bn == 128) rc = launch<128>(ma, mb, y, p, static_cast<int>(mtiles), st);
-    else if (bn == 64) rc = launch<64>(ma, mb, y, p, static_cast<int>(mtiles), st);
-    else rc = launch<32>(ma, mb, y, p, static_cast<int>(mtiles), st);
+    if (!x3) { ma2 = ma; mb2 = mb; }
+    rc = launch_any(bn, x3, ma, ma2, mb, mb2, y, p, static_cast<int>(mtiles), st);
     if (mode != 2 || rc != GIFB200_OK) return rc;
     // ---- T2 border: output row Y = 2*Hi and column X = 2*Wi (the sites y = Hi / x = Wi that the power-of-two site grid does
     // not cover).  Row Y = 2*Hi only sees kernel row kh = 2 applied to input row Hi-1: a 1-D transposed convolution along x;
@@ -444,23 +526,31 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
             }
             q.phase_ntaps[ph] = n;
         }
-        CUtensorMap me;
-        const float* base = x + (row ? static_cast<long long>(Hi - 1) * Wi * Ci : static_cast<long long>(Wi - 1) * Ci);
+        CUtensorMap me, me2;
+        const char* base = xb + (row ? static_cast<long long>(Hi - 1) * Wi * Ci : static_cast<long long>(Wi - 1) * Ci) * es;
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Ci), static_cast<cuuint64_t>(row ? Wi : 1),
                                     static_cast<cuuint64_t>(row ? 1 : Hi), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * 4, static_cast<cuuint64_t>(Wi) * Ci * 4,
-                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * 4};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Ci) * es, static_cast<cuuint64_t>(Wi) * Ci * es,
+                                       static_cast<cuuint64_t>(Hi) * Wi * Ci * es};
         const cuuint32_t box[4] = {kBlockK, static_cast<cuuint32_t>(q.wt), static_cast<cuuint32_t>(q.ht), static_cast<cuuint32_t>(q.nt)};
-        rc = encode_map(&me, base, 4, dims, strides, box);
+        rc = encode_map(&me, base, 4, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&me2, base + x_plane * es, 4, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
-        if (bn == 128) rc = launch<128>(me, mb, y, q, static_cast<int>(mt_e), st);
-        else if (bn == 64) rc = launch<64>(me, mb, y, q, static_cast<int>(mt_e), st);
-        else rc = launch<32>(me, mb, y, q, static_cast<int>(mt_e), st);
+        if (!x3) me2 = me;
+        rc = launch_any(bn, x3, me, me2, mb, mb2, y, q, static_cast<int>(mt_e), st);
     }
     if (rc != GIFB200_OK) return rc;
-    t2_corner_kernel<<<cdiv(static_cast<long long>(B) * Co * 32, 256), 256, 0, st>>>(
-        x + (static_cast<long long>(Hi - 1) * Wi + (Wi - 1)) * Ci, wst + static_cast<long long>(8) * Co * Ci, y, B,
-        static_cast<long long>(Hi) * Wi * Ci, Ci, Co, Ho, Wo, epi);
+    {
+        const char* xpix = xb + (static_cast<long long>(Hi - 1) * Wi + (Wi - 1)) * Ci * es;
+        const char* w22 = wb + static_cast<long long>(8) * Co * Ci * es;
+        const int blocks = cdiv(static_cast<long long>(B) * Co * 32, 256);
+        if (x3)
+            t2_corner_kernel<true><<<blocks, 256, 0, st>>>(xpix, w22, y, B, static_cast<long long>(Hi) * Wi * Ci, Ci, Co, Ho, Wo,
+                                                           epi, x_plane, w_plane);
+        else
+            t2_corner_kernel<false><<<blocks, 256, 0, st>>>(xpix, w22, y, B, static_cast<long long>(Hi) * Wi * Ci, Ci, Co, Ho, Wo,
+                                                            epi, 0, 0);
+    }
     GIFB200_LAUNCH_CHECK("t2_corner_kernel");
     return rc;
 }

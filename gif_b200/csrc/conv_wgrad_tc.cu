@@ -17,6 +17,11 @@
 // so the four 32-row chunks of the A tile hold the SAME 32 channels of S at three different row shifts (dy = +1, 0, -1;
 // the 4th chunk is a duplicate) -- chunk kh then accumulates kernel row kh, the KW shifted Bg tiles give the kernel
 // columns, and ONE CTA produces all 9 taps (no kh split).
+//
+// X3 = true ("bf16x3", gifb200_conv2d_wgrad impl 3): both operands arrive as two bf16 planes (hi, lo; gifb200_split_bf16).
+// 16-bit MN-major tiles of 32 channels use the canonical SWIZZLE_64B layout (rows of 64 bytes, 8-pixel K atoms of 512 B; TMA
+// side CU_TENSOR_MAP_SWIZZLE_64B); a stage holds the hi and the lo chunk set of each operand -- the SAME bytes as the fp32
+// tiles -- and every 16-pixel slice issues three kind::f16 MMAs (lo*hi, hi*lo, hi*hi) into the tap's fp32 TMEM accumulator.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -26,7 +31,6 @@ namespace {
 
 constexpr int kWgStages = 3;
 constexpr int kPix = 32;                       // pixels (GEMM K) per stage
-constexpr int kChunkBytes = kPix * 128;        // one 32-channel x 32-pixel chunk = 4 KB
 constexpr int kAChunks = 4;                    // M = 128 small channels
 
 struct WgParams {
@@ -40,42 +44,53 @@ struct WgParams {
     long long part_stride;   // floats per split in the partial buffer: T * Cs_total * Cb (layout [split][t][cs][cb])
 };
 
-__device__ __forceinline__ uint64_t make_mnmajor_sw128b32_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                               uint32_t base_offset = 0) {
+// MN-major descriptor.  fp32: LayoutType::SWIZZLE_128B_BASE32B (1), 4-pixel K atoms of 512 B.  bf16 (X3):
+// LayoutType::SWIZZLE_64B (4), 8-pixel K atoms of 8 x 64 B = 512 B.  Either way SBO = 512 B and LBO = chunk distance.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t layout_type,
+                                                      uint32_t base_offset = 0) {
     uint64_t d = static_cast<uint64_t>(base_offset & 7) << 49;   // swizzle-phase of a start address inside an atom
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;       // between 32-channel (MN) chunks
-    d |= static_cast<uint64_t>(512 >> 4) << 32;             // between 4-pixel (K) swizzle atoms
+    d |= static_cast<uint64_t>(512 >> 4) << 32;             // between K swizzle atoms
     d |= static_cast<uint64_t>(1) << 46;                    // descriptor version (sm_100)
-    d |= static_cast<uint64_t>(1) << 61;                    // LayoutType::SWIZZLE_128B_BASE32B
+    d |= static_cast<uint64_t>(layout_type) << 61;
     return d;
 }
 
 constexpr int kHaloRows = kPix + 2;                 // 34 pixel rows: the 32 of the stage + one on each side
-constexpr int kHaloChunkBytes = 4608;               // 34 * 128 B padded to a multiple of the 512 B swizzle atom
 
 // HALO (stride-1 layers with Ws >= 32): the KW shifted big-tensor tiles of a stage overlap in all but 2 pixel rows, so the
 // stage holds ONE (32 + 2)-row tile per 32-channel chunk and tap kw addresses it at row offset kw (start address + kw*128 B).
 // 35 KB instead of 64 KB per stage -> a 5-deep ring instead of 3 and 8 instead of 16 TMA issues.
-template <int KW, int BLOCK_N, bool HALO = false>
+template <int KW, int BLOCK_N, bool HALO = false, bool X3 = false>
 struct WgSmem {
+    static constexpr int kRowBytes = X3 ? 64 : 128;                   // 32 channels of one pixel
+    static constexpr int kChunkBytes = kPix * kRowBytes;              // one 32-channel x 32-pixel chunk: 4 KB fp32, 2 KB bf16
+    static constexpr int kHaloChunkBytes = X3 ? 2560 : 4608;          // 34 rows padded to a multiple of the 512 B swizzle atom
+    static constexpr int kPlanes = X3 ? 2 : 1;                        // hi and lo chunk sets, hi first
     static constexpr int kBChunks = BLOCK_N / 32;
-    static constexpr int kABytes = kAChunks * kChunkBytes;
-    static constexpr int kBBytesPerTap = kBChunks * kChunkBytes;
+    static constexpr int kAPlaneBytes = kAChunks * kChunkBytes;
+    static constexpr int kABytes = kPlanes * kAPlaneBytes;
+    static constexpr int kBPlaneBytes = kBChunks * (HALO ? kHaloChunkBytes : kChunkBytes);   // one tap (or the halo tile), one plane
+    static constexpr int kBBytesPerTap = kPlanes * kBPlaneBytes;
     static constexpr int kStages = HALO ? 5 : kWgStages;
-    static constexpr int kStageBytes = HALO ? kABytes + kBChunks * kHaloChunkBytes : kABytes + KW * kBBytesPerTap;
-    static constexpr int kTxBytes = HALO ? kABytes + kBChunks * kHaloRows * 128 : kStageBytes;
+    static constexpr int kStageBytes = HALO ? kABytes + kBBytesPerTap : kABytes + KW * kBBytesPerTap;
+    static constexpr int kTxBytes = HALO ? kABytes + kPlanes * kBChunks * kHaloRows * kRowBytes : kStageBytes;
     static constexpr int kBarrierOffset = (kStages * kStageBytes + 1023) / 1024 * 1024;
     static constexpr int kDynamic = kBarrierOffset + 128 + 1024;
     static constexpr int kTmemCols = (KW * BLOCK_N <= 32) ? 32 : (KW * BLOCK_N <= 64) ? 64 : (KW * BLOCK_N <= 128) ? 128
                                      : (KW * BLOCK_N <= 256) ? 256 : 512;
 };
 
-template <int KW, int BLOCK_N, bool STACK, bool HALO>
+template <int KW, int BLOCK_N, bool STACK, bool HALO, bool X3>
 __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_s,
+                                                          const __grid_constant__ CUtensorMap map_s2,
                                                           const __grid_constant__ CUtensorMap map_b,
+                                                          const __grid_constant__ CUtensorMap map_b2,
                                                           float* __restrict__ part, const WgParams p) {
-    using L = WgSmem<KW, BLOCK_N, HALO>;
+    using L = WgSmem<KW, BLOCK_N, HALO, X3>;
+    constexpr int kChunkBytes = L::kChunkBytes;
+    constexpr int kHaloChunkBytes = L::kHaloChunkBytes;
     constexpr int kNStages = L::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -96,6 +111,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_s) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (X3) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_s2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b2) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kNStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -120,7 +139,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
             const bool first = warp == 0;
             const int rows = kPix / p.pw;                    // rows of the small grid per stage
             const int segs = p.Ws / p.pw;                    // 32-pixel segments per row (>= 1 when pw == 32)
-            const int row_bytes = p.pw * 128;
+            const int row_bytes = p.pw * L::kRowBytes;
             int stage = 0;
             uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
@@ -135,54 +154,73 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                     if (rows == 1) { grow = u / segs; x0 = static_cast<int>(u % segs) * kPix; }
                     else { grow = u * rows + r; x0 = 0; }
                     const int n = static_cast<int>(grow / p.Hs), y = static_cast<int>(grow % p.Hs);
-                    if (first) {
-                        for (int c = 0; c < kAChunks; ++c) {
-                            if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
-                                tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], 0, x0,
-                                            y + 1 - (c < 3 ? c : 2), n);
-                            else
-                                tma_load_4d(a_dst + c * kChunkBytes + r * row_bytes, &map_s, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+#pragma unroll
+                    for (int pl = 0; pl < L::kPlanes; ++pl) {    // X3: plane 0 = hi, plane 1 = lo (same coordinates, own map)
+                        const CUtensorMap* ms_ = pl ? &map_s2 : &map_s;
+                        const CUtensorMap* mb_ = pl ? &map_b2 : &map_b;
+                        uint8_t* a_pl = a_dst + pl * L::kAPlaneBytes;
+                        if (first) {
+                            for (int c = 0; c < kAChunks; ++c) {
+                                if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
+                                    tma_load_4d(a_pl + c * kChunkBytes + r * row_bytes, ms_, &full_bar[stage], 0, x0,
+                                                y + 1 - (c < 3 ? c : 2), n);
+                                else
+                                    tma_load_4d(a_pl + c * kChunkBytes + r * row_bytes, ms_, &full_bar[stage], ms * 128 + c * 32, x0, y, n);
+                            }
                         }
-                    }
-                    if (HALO) {      // one (32+2)-pixel tile per 32-channel chunk, starting one pixel to the left
-                        for (int c = 0; c < L::kBChunks; ++c)
-                            tma_load_4d(b_dst + c * kHaloChunkBytes, &map_b, &full_bar[stage], nb * BLOCK_N + c * 32, x0 - 1,
-                                        y + (STACK ? 0 : kh - p.pad), n);
-                        continue;
-                    }
-                    for (int kw = first ? 0 : 1; kw < (first ? 1 : KW); ++kw)
-                        for (int c = 0; c < L::kBChunks; ++c) {
-                            uint8_t* dst = b_dst + kw * L::kBBytesPerTap + c * kChunkBytes + r * row_bytes;
-                            const int ch = nb * BLOCK_N + c * 32;
-                            if (STACK)
-                                tma_load_4d(dst, &map_b, &full_bar[stage], ch, x0 + kw - 1, y, n);
-                            else if (!p.s2)
-                                tma_load_4d(dst, &map_b, &full_bar[stage], ch, x0 + kw - p.pad, y + kh - p.pad, n);
-                            else
-                                tma_load_5d(dst, &map_b, &full_bar[stage], ch, kw & 1, x0 + (kw >> 1), 2 * y + kh, n);
+                        if (HALO) {      // one (32+2)-pixel tile per 32-channel chunk, starting one pixel to the left
+                            for (int c = 0; c < L::kBChunks; ++c)
+                                tma_load_4d(b_dst + pl * L::kBPlaneBytes + c * kHaloChunkBytes, mb_, &full_bar[stage],
+                                            nb * BLOCK_N + c * 32, x0 - 1, y + (STACK ? 0 : kh - p.pad), n);
+                            continue;
                         }
+                        for (int kw = first ? 0 : 1; kw < (first ? 1 : KW); ++kw)
+                            for (int c = 0; c < L::kBChunks; ++c) {
+                                uint8_t* dst = b_dst + kw * L::kBBytesPerTap + pl * L::kBPlaneBytes + c * kChunkBytes + r * row_bytes;
+                                const int ch = nb * BLOCK_N + c * 32;
+                                if (STACK)
+                                    tma_load_4d(dst, mb_, &full_bar[stage], ch, x0 + kw - 1, y, n);
+                                else if (!p.s2)
+                                    tma_load_4d(dst, mb_, &full_bar[stage], ch, x0 + kw - p.pad, y + kh - p.pad, n);
+                                else
+                                    tma_load_5d(dst, mb_, &full_bar[stage], ch, kw & 1, x0 + (kw >> 1), 2 * y + kh, n);
+                            }
+                    }
                 }
                 if (++stage == kNStages) { stage = 0; ph ^= 1; }
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
             // MN-major operands: a_major = b_major = 1 (bits 15, 16)
-            constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N) | (1u << 15) | (1u << 16);
+            constexpr uint32_t idesc = (X3 ? make_idesc_bf16(128, BLOCK_N) : make_idesc_tf32(128, BLOCK_N)) | (1u << 15) | (1u << 16);
+            constexpr uint32_t kLayout = X3 ? 4u : 1u;       // SWIZZLE_64B (bf16) / SWIZZLE_128B_BASE32B (fp32)
+            constexpr uint32_t kBLbo = HALO ? kHaloChunkBytes : kChunkBytes;
             int stage = 0;
             uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(&full_bar[stage], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-                const uint64_t adesc = make_mnmajor_sw128b32_desc(a_addr, kChunkBytes);
+                const uint64_t adesc = make_mnmajor_desc(a_addr, kChunkBytes, kLayout);
+                const uint64_t adesc_lo = make_mnmajor_desc(a_addr + L::kAPlaneBytes, kChunkBytes, kLayout);
 #pragma unroll
                 for (int kw = 0; kw < KW; ++kw) {
-                    const uint64_t bdesc = HALO
-                        ? make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * 128, kHaloChunkBytes, p.halo_bo ? kw : 0)
-                        : make_mnmajor_sw128b32_desc(a_addr + L::kABytes + kw * L::kBBytesPerTap, kChunkBytes);
+                    // HALO: tap kw reads the one halo tile kw pixel rows further in
+                    const uint32_t b_addr = a_addr + L::kABytes + (HALO ? kw * L::kRowBytes : kw * L::kBBytesPerTap);
+                    const uint64_t bdesc = make_mnmajor_desc(b_addr, kBLbo, kLayout, (HALO && !X3 && p.halo_bo) ? kw : 0);
+                    if (X3) {
+                        const uint64_t bdesc_lo = make_mnmajor_desc(b_addr + L::kBPlaneBytes, kBLbo, kLayout);
 #pragma unroll
-                    for (int j = 0; j < kPix / 8; ++j)   // 8 pixels per MMA: next swizzle atom = +1024 B (>>4 = 64)
-                        umma_tf32(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
+                        for (int j = 0; j < kPix / 16; ++j) {   // 16 pixels per MMA = two 8-pixel atoms: next slice = +1024 B (>>4 = 64)
+                            umma_bf16(tmem_base + kw * BLOCK_N, adesc_lo + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
+                            umma_bf16(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc_lo + 64 * j, idesc, 1);
+                            umma_bf16(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kPix / 8; ++j)   // 8 pixels per MMA: next swizzle atom = +1024 B (>>4 = 64)
+                            umma_tf32(tmem_base + kw * BLOCK_N, adesc + 64 * j, bdesc + 64 * j, idesc, (it | j) != 0);
+                    }
                 }
                 umma_commit(&empty_bar[stage]);
                 if (++stage == kNStages) { stage = 0; ph ^= 1; }
@@ -264,17 +302,19 @@ int pick_bn(int Cb) {
     return 0;
 }
 
-template <int KW, int BLOCK_N, bool STACK, bool HALO>
-int launch_wg(const CUtensorMap& ms, const CUtensorMap& mb, float* out, float* part, const WgParams& p, cudaStream_t st) {
-    using L = WgSmem<KW, BLOCK_N, HALO>;
+struct WgMaps { CUtensorMap s, s2, b, b2; };
+
+template <int KW, int BLOCK_N, bool STACK, bool HALO, bool X3>
+int launch_wg(const WgMaps& m, float* out, float* part, const WgParams& p, cudaStream_t st) {
+    using L = WgSmem<KW, BLOCK_N, HALO, X3>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(wgrad_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
     dim3 grid(STACK ? 1 : p.Cs / 128, p.Cb / BLOCK_N, STACK ? p.splits : p.k * p.splits);
-    wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO><<<grid, 256, L::kDynamic, st>>>(ms, mb, part, p);
+    wgrad_tc_kernel<KW, BLOCK_N, STACK, HALO, X3><<<grid, 256, L::kDynamic, st>>>(m.s, m.s2, m.b, m.b2, part, p);
     GIFB200_LAUNCH_CHECK("wgrad_tc_kernel");
     const int T = p.k * p.k;
     const long long total = static_cast<long long>(T) * p.Cs * p.Cb;
@@ -330,8 +370,19 @@ size_t conv2d_wgrad_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, in
     return static_cast<size_t>(wgrad_splits(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, nullptr)) * k * k * Co * Ci * sizeof(float) + 256;
 }
 
+template <bool X3>
+static int dispatch_wg(int k, int bn, bool stack, bool halo, const WgMaps& m, float* gw, float* part, const WgParams& p, cudaStream_t st) {
+#define GIFB200_WG(KW, BN, ST, HA) launch_wg<KW, BN, ST, HA, X3>(m, gw, part, p, st)
+    if (stack && halo) return bn == 128 ? GIFB200_WG(3, 128, true, true) : bn == 64 ? GIFB200_WG(3, 64, true, true) : GIFB200_WG(3, 32, true, true);
+    if (stack) return bn == 128 ? GIFB200_WG(3, 128, true, false) : bn == 64 ? GIFB200_WG(3, 64, true, false) : GIFB200_WG(3, 32, true, false);
+    if (halo) return bn == 128 ? GIFB200_WG(3, 128, false, true) : bn == 64 ? GIFB200_WG(3, 64, false, true) : GIFB200_WG(3, 32, false, true);
+    if (k == 3) return bn == 128 ? GIFB200_WG(3, 128, false, false) : bn == 64 ? GIFB200_WG(3, 64, false, false) : GIFB200_WG(3, 32, false, false);
+    return bn == 128 ? GIFB200_WG(1, 128, false, false) : bn == 64 ? GIFB200_WG(1, 64, false, false) : GIFB200_WG(1, 32, false, false);
+#undef GIFB200_WG
+}
+
 int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,
-                    int k, int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int k, int mode, int flip, int transposed, void* ws, size_t ws_bytes, cudaStream_t st, bool x3) {
     GIFB200_REQUIRE(ws && ws_bytes >= conv2d_wgrad_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_WORKSPACE,
                     "conv2d_wgrad_tc: workspace too small (see gifb200_conv2d_wgrad_workspace_bytes)");
     float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
@@ -357,13 +408,22 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
     const bool stack = (p.Cs == 32 && mode == 0 && k == 3);
     p.splits = static_cast<int>(wgrad_splits(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, nullptr));
     p.part_stride = static_cast<long long>(k) * k * Co * Ci;
-    CUtensorMap ms, mb;
+    // operand element size / tile layout: fp32 (MN-major SWIZZLE_128B_BASE32B) or bf16 planes (MN-major SWIZZLE_64B)
+    const cuuint64_t es = x3 ? 2 : 4;
+    const CUtensorMapSwizzle swz = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const CUtensorMapDataType dt = x3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const char* Sb = reinterpret_cast<const char*>(S);
+    const char* Bb = reinterpret_cast<const char*>(Bg);
+    const long long s_plane = static_cast<long long>(B) * p.Hs * p.Ws * p.Cs * es;   // bytes between the hi and the lo plane
+    const long long b_plane = static_cast<long long>(B) * p.Hb * p.Wb * p.Cb * es;
+    WgMaps m;
     {
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cs), static_cast<cuuint64_t>(p.Ws), static_cast<cuuint64_t>(p.Hs), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cs) * 4, static_cast<cuuint64_t>(p.Ws) * p.Cs * 4,
-                                       static_cast<cuuint64_t>(p.Hs) * p.Ws * p.Cs * 4};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cs) * es, static_cast<cuuint64_t>(p.Ws) * p.Cs * es,
+                                       static_cast<cuuint64_t>(p.Hs) * p.Ws * p.Cs * es};
         const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&ms, S, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = encode_map(&m.s, Sb, 4, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&m.s2, Sb + s_plane, 4, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
     }
     // GIFB200_WGRAD_HALO: 0 = off, 1 = on (default).  Measured on B200: a tile start address that is a whole number of
@@ -374,32 +434,23 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
     p.halo_bo = halo_env == 2;
     if (!p.s2) {
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cb), static_cast<cuuint64_t>(p.Wb), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Wb) * p.Cb * 4,
-                                       static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * es, static_cast<cuuint64_t>(p.Wb) * p.Cb * es,
+                                       static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * es};
         const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(halo ? kHaloRows : p.pw), 1, 1};
-        int rc = encode_map(&mb, Bg, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = encode_map(&m.b, Bb, 4, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&m.b2, Bb + b_plane, 4, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
     } else {
         const cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.Cb), 2, static_cast<cuuint64_t>((p.Wb + 1) / 2), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(p.Cb) * 4, static_cast<cuuint64_t>(p.Cb) * 8,
-                                       static_cast<cuuint64_t>(p.Wb) * p.Cb * 4, static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * 4};
+        const cuuint64_t strides[4] = {static_cast<cuuint64_t>(p.Cb) * es, static_cast<cuuint64_t>(p.Cb) * 2 * es,
+                                       static_cast<cuuint64_t>(p.Wb) * p.Cb * es, static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * es};
         const cuuint32_t box[5] = {32, 1, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&mb, Bg, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        int rc = encode_map(&m.b, Bb, 5, dims, strides, box, swz, dt);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&m.b2, Bb + b_plane, 5, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
     }
-#define GIFB200_WG(KW, BN) launch_wg<KW, BN, false, false>(ms, mb, gw, part, p, st)
-    if (stack && halo)
-        return bn == 128 ? launch_wg<3, 128, true, true>(ms, mb, gw, part, p, st)
-               : bn == 64 ? launch_wg<3, 64, true, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true, true>(ms, mb, gw, part, p, st);
-    if (stack)
-        return bn == 128 ? launch_wg<3, 128, true, false>(ms, mb, gw, part, p, st)
-               : bn == 64 ? launch_wg<3, 64, true, false>(ms, mb, gw, part, p, st) : launch_wg<3, 32, true, false>(ms, mb, gw, part, p, st);
-    if (halo)
-        return bn == 128 ? launch_wg<3, 128, false, true>(ms, mb, gw, part, p, st)
-               : bn == 64 ? launch_wg<3, 64, false, true>(ms, mb, gw, part, p, st) : launch_wg<3, 32, false, true>(ms, mb, gw, part, p, st);
-    if (k == 3) return bn == 128 ? GIFB200_WG(3, 128) : bn == 64 ? GIFB200_WG(3, 64) : GIFB200_WG(3, 32);
-    return bn == 128 ? GIFB200_WG(1, 128) : bn == 64 ? GIFB200_WG(1, 64) : GIFB200_WG(1, 32);
-#undef GIFB200_WG
+    if (!x3) { m.s2 = m.s; m.b2 = m.b; }
+    return x3 ? dispatch_wg<true>(k, bn, stack, halo, m, gw, part, p, st) : dispatch_wg<false>(k, bn, stack, halo, m, gw, part, p, st);
 }
 
 }  // namespace gifb200

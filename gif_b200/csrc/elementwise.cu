@@ -1,5 +1,7 @@
 // Memory-bound elementwise / reduction kernels of the StyleGAN2 hot path (channels-last fp32).
 // Roofline for all of them is HBM: algorithmic bytes = inputs read once + outputs written once.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gifb200 {
@@ -325,6 +327,40 @@ __global__ void __launch_bounds__(256) chan_scale_kernel(const float* __restrict
             float t = x[i] * s[((i / C) / P) * C + (i % C)];
             y[i] = rtf32 ? round_tf32(t) : t;
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ split (bf16x3 operands)
+// planes[0][e] = bf16_rn(v), planes[1][e] = bf16_rn(v - planes[0][e]) with v = x[e] * (s ? s[b,c] : 1): the two-term bf16
+// expansion (16 significant bits) the compensated tensor-core contraction reads (conv_tc.cu / conv_wgrad_tc.cu, X3 mode).
+// One pass: 4 B in, 2 x 2 B out per element; with s it also IS the modulation pass (no fp32 copy of the modulated input).
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                         __nv_bfloat16* __restrict__ planes, long long total, int P, int C) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long nvec = total >> 2;
+    const int c4n = C >> 2;
+    __nv_bfloat16* hi = planes;
+    __nv_bfloat16* lo = planes + total;
+    for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        float4 t = __ldcs(reinterpret_cast<const float4*>(x) + v);
+        if (s) {
+            const int c = static_cast<int>(v % c4n) << 2;
+            const long long b = (v / c4n) / P;
+            const float4 sc = *reinterpret_cast<const float4*>(s + b * C + c);
+            t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
+        }
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(t.x), h1 = __float2bfloat16_rn(t.y), h2 = __float2bfloat16_rn(t.z),
+                            h3 = __float2bfloat16_rn(t.w);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(t.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(t.y - __bfloat162float(h1)),
+                            l2 = __float2bfloat16_rn(t.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(t.w - __bfloat162float(h3));
+        uint2 ph, pl;
+        ph.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        ph.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+        pl.x = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+        pl.y = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+        reinterpret_cast<uint2*>(hi)[v] = ph;
+        reinterpret_cast<uint2*>(lo)[v] = pl;
     }
 }
 
@@ -774,6 +810,17 @@ int gifb200_chan_scale(const float* x, const float* s, float* y, int B, int P, i
     else
         chan_scale_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(x, s, y, total, P, C, rtf32);
     GIFB200_LAUNCH_CHECK("chan_scale_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_split_bf16(const float* x, const float* s, void* planes, int B, int P, int C, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0 && C % 4 == 0, GIFB200_E_SHAPE, "split_bf16: C must be a positive multiple of 4");
+    const long long total = static_cast<long long>(B) * P * C;
+    if (total == 0) return GIFB200_OK;
+    GIFB200_REQUIRE(aligned16(x) && aligned16(planes) && (!s || aligned16(s)), GIFB200_E_ALIGN, "split_bf16: pointers must be 16-byte aligned");
+    split_bf16_kernel<<<grid_for(total / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, s, static_cast<__nv_bfloat16*>(planes), total, P, C);
+    GIFB200_LAUNCH_CHECK("split_bf16_kernel");
     return GIFB200_OK;
 }
 

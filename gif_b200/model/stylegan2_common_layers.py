@@ -110,10 +110,10 @@ def _conv_mode(kernel_size, stride, padding):
 
 
 def _pad_channels_for_tc(x, wt):
-    """tf32 mode: zero-pad the input channels (and the weight's Ci) to a multiple of 32 so that odd-channel layers (the
+    """tensor-core modes (tf32 / bf16x3): zero-pad the input channels (and the weight's Ci) to a multiple of 32 so that odd-channel layers (the
     9-channel discriminator stem, the 513-channel minibatch-stddev conv) run on the tcgen05 kernels; values unchanged."""
     ci = x.shape[-1]
-    if ops.tf32_enabled() and ci % 32 != 0 and wt.shape[1] % 32 == 0:
+    if ops.tc_enabled() and ci % 32 != 0 and wt.shape[1] % 32 == 0:
         pad = 32 - ci % 32
         x = F.pad(x, (0, pad))
         wt = F.pad(wt, (0, pad))
@@ -284,7 +284,7 @@ class NoiseInjection(nn.Module):
         c0, c2, c4 = self.noise_conv[0], self.noise_conv[2], self.noise_conv[4]
         w0, w2, w4 = ops.prep_weight(c0.weight), ops.prep_weight(c2.weight), ops.prep_weight(c4.weight)
         b0, b2 = c0.bias, c2.bias
-        if ops.tf32_enabled() and noise.shape[1] >= 4 and (noise.shape[1] & (noise.shape[1] - 1)) == 0:
+        if ops.tc_enabled() and noise.shape[1] >= 4 and (noise.shape[1] & (noise.shape[1] - 1)) == 0:
             def up32(n):
                 return (n + 31) // 32 * 32
             ci, c1, c2n = w0.shape[2], w0.shape[1], w2.shape[1]

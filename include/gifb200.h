@@ -58,7 +58,12 @@ long long gifb200_launch_count(void);
  *     adj(S1, flip, tr) = (S1, !flip, !tr);  adj(S2, flip, tr) = (T2, flip, !tr);  adj(T2, flip, tr) = (S2, flip, !tr).
  *
  * impl: 0 = auto (tcgen05 tensor-core path when the shape qualifies, else SIMT), 1 = force SIMT fp32,
- *       2 = force tcgen05 (kind::tf32, fp32 accumulate; returns GIFB200_E_SHAPE if the shape does not qualify).
+ *       2 = force tcgen05 (kind::tf32, fp32 accumulate; returns GIFB200_E_SHAPE if the shape does not qualify),
+ *       3 = tcgen05 ERROR-COMPENSATED contraction ("bf16x3", fp32 accumulate): every operand is the two-term bf16
+ *           expansion v = hi + lo written by gifb200_split_bf16 and the kernel accumulates hi*hi + hi*lo + lo*hi into the
+ *           same TMEM accumulator (16 significant operand bits, ~1e-5 relative; 1.5x the tensor work of kind::tf32).
+ *           With impl 3, `x` is NOT an fp32 tensor but the planes buffer of gifb200_split_bf16 for the input
+ *           (2 x B*Hi*Wi*Ci bf16 = the same number of bytes); w stays fp32 (split while staging).  Same shapes as impl 2.
  * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL).
  * Fused epilogue (ConvLayer = EqualConv2d -> FusedLeakyReLU, cl.py:752-799; nn.Conv2d + ReLU of NoiseInjection):
  *     y = lrelu(acc + bias[o], slope) * gain, optionally rounded to tf32;  act == 0 writes the plain accumulator
@@ -74,7 +79,8 @@ int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int 
  *     gW[t,o,i] = sum_{b,pixels} gy[b,p_out,o] * x[b,p_in(p_out,t),i]   (p_in as in the mode's formula above)
  * x is the conv input (B,Hi,Wi,Ci), gy the conv output gradient (B,Ho,Wo,Co).  gw is OVERWRITTEN.
  * Replaces autograd's conv weight gradient for the reference modules listed above.
- * impl: 0 auto, 1 SIMT fp32, 2 tcgen05 on the channels-last operands (MN-major tiles). */
+ * impl: 0 auto, 1 SIMT fp32, 2 tcgen05 kind::tf32 on the channels-last operands (MN-major tiles), 3 = bf16x3 compensated
+ * contraction: BOTH x and gy are planes buffers of gifb200_split_bf16 (see gifb200_conv2d). */
 size_t gifb200_conv2d_wgrad_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
                                             int impl);
 /* which kernel gifb200_conv2d_wgrad will run for this shape / impl request: 1 or 2 as above (0: request not possible).
@@ -83,6 +89,12 @@ int gifb200_conv2d_wgrad_path(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int
 int gifb200_conv2d_wgrad(const float* x, const float* gy, float* gw, int B, int Hi, int Wi, int Ci, int Ho, int Wo,
                          int Co, int k, int mode, int flip, int transposed, int impl, void* workspace,
                          size_t workspace_bytes, gifb200_stream_t stream);
+
+/* Two-term bf16 expansion of an fp32 tensor (B, P pixels, C channels, channels-last), optionally fused with the style
+ * modulation of ModulatedConv2d (cl.py:311-313 in the modulate-input form): v = x[b,p,c] * (s ? s[b,c] : 1);
+ *     planes[0][b,p,c] = bf16_rn(v);   planes[1][b,p,c] = bf16_rn(v - planes[0][b,p,c])
+ * planes: 2 * B*P*C bf16 (16-byte aligned).  The operand format of impl 3 above.  C % 4 == 0. */
+int gifb200_split_bf16(const float* x, const float* s, void* planes, int B, int P, int C, gifb200_stream_t stream);
 
 /* ---- upfirdn2d ---------------------------------------------------------------------------------------
  * Replaces upfirdn2d (cl.py:42-72) and through it Blur (cl.py:136-152), Upsample (cl.py:94-112),

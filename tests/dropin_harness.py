@@ -69,14 +69,14 @@ def make_args():
         apply_texture_space_interpolation_loss=False, adaptive_interp_loss=False, use_posed_constant_input=False, run_id="t")
 
 
-def _loader(n_iters):
+def _loader(n_iters, first_i=0):
     def sample_data(dataset, batch_size, image_sizes, debug=False):
         assert batch_size == BATCH and image_sizes[-1] == RES
 
         class Loader:
             def __iter__(self):
                 def gen():
-                    for i in range(n_iters):
+                    for i in range(first_i, first_i + n_iters):
                         real, cond, lbls, idx = batch(i)
                         yield real, [cond], [lbls], idx
                     raise StopTraining()
@@ -122,13 +122,16 @@ def build_networks(gen_mod, disc_mod, device):
     return G.to(device), D.to(device), Gr.to(device)
 
 
-def run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after=(1,)):
-    """Runs train_mod.train() for n_iters iterations.  Returns {k: snapshot} for k in snapshot_after + (n_iters,)."""
+def run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after=(1,), first_i=0):
+    """Runs train_mod.train() for n_iters iterations.  Returns {k: snapshot} for k in snapshot_after + (n_iters,).
+    ``first_i``: the value train()'s loop counter starts from -- train.py:79 iterates ``tqdm(range(3_000_000))`` and the
+    harness supplies the ``tqdm`` stand-in, so it can hand the loop ``range(first_i, ...)``: with first_i = 15 the FIRST
+    iteration is an R1 iteration (``(i + 1) % 16 == 0``, train.py:145) of the unmodified function."""
     with cuda_calls_are_noops_without_a_gpu():
-        return _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after)
+        return _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after, first_i)
 
 
-def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after):
+def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after, first_i):
     from torch import nn, optim
     generator = nn.DataParallel(G).cuda()                  # train.py:344 (the drop-in's stand-in when it is installed)
     discriminator = nn.DataParallel(D).cuda()              # train.py:356
@@ -139,7 +142,7 @@ def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after):
     train_mod.d_optimizer_flm = optim.Adam(discriminator.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
     train_mod.g_running = g_running
     train_mod.n_critic = 1                                 # train.py:322
-    train_mod.sample_data = _loader(n_iters)
+    train_mod.sample_data = _loader(n_iters, first_i)
     snaps = {}
 
     def snap(done):
@@ -152,7 +155,7 @@ def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after):
             self.it = it
 
         def __iter__(self):
-            return iter(self.it)
+            return iter(range(first_i, len(self.it)))
 
         def set_description(self, *_a, **_k):
             pass
@@ -191,18 +194,21 @@ def flatten_snaps(snaps):
     return {f"it{k}|{n}": v for k, s in snaps.items() for n, v in s.items()}
 
 
-def compare(snap, golden, it, tol_d, tol_g, tol_moment):
-    """L2-relative deviation of every watched tensor from the golden (parameters: relative to the parameter norm)."""
+def compare(snap, golden, it, tol_d, tol_g, tol_moment, floor_factor=3.0, scenario=""):
+    """L2-relative deviation of every watched tensor from the golden.  The bar of a tensor is max(the net's bar,
+    floor_factor x the reference's OWN fp32-vs-fp64 deviation for that tensor at that iteration) -- the golden stores the
+    float64 run of the same unmodified train() beside the float32 one, so the chaotic part of a 16-step Adam trajectory
+    (tiny tensors such as a 3-element to_rgb bias flip whole +-lr steps) is measured, not guessed."""
     worst = {}
     for key, got in snap.items():
         if key.endswith("|norm"):
             continue
-        ref = golden[f"it{it}|{key}"]
+        ref = golden[f"{scenario}it{it}|{key}"]
+        ref64 = golden[f"f64|{scenario}it{it}|{key}"]
+        floor = float(np.linalg.norm(ref - ref64) / max(np.linalg.norm(ref64), 1e-300))
         tag = key.split("|")[0]
-        if key.endswith("exp_avg_sq"):
-            err, tol = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300), tol_moment
-        else:
-            err, tol = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300), (tol_d if tag == "d" else tol_g)
-        worst[key] = (float(err), tol)
+        base = tol_moment if key.endswith("exp_avg_sq") else (tol_d if tag == "d" else tol_g)
+        err = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
+        worst[key] = (err, max(base, floor_factor * floor))
     bad = {k: v for k, v in worst.items() if not v[0] < v[1]}
     return worst, bad

@@ -110,3 +110,83 @@ def test_wgrad_tc_matches_simt(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transpose
     assert res[0].shape == res[1].shape
     e = gu.rel_err(res[0].cpu().numpy(), res[1].cpu().numpy())
     assert e < 5e-5, e
+
+
+# ------------------------------------------------------------------------------------------------ bf16x3 (compensated)
+# The error-compensated mode (gifb200_conv2d / _wgrad impl 3): UNROUNDED fp32 operands, split into two bf16 terms by
+# gifb200_split_bf16, hi*hi + hi*lo + lo*hi on kind::f16, fp32 accumulate.  Expected error ~2^-17 per operand (the dropped
+# lo*lo term and the rounding of lo): the bar is 5e-5 against the exact-fp32 SIMT kernel on the same raw inputs -- 20x
+# inside BASELINE.json's 1e-3 and 6x inside what kind::tf32 can do (3e-4).
+def test_split_bf16_planes(cuda):
+    from gif_b200 import ops
+    x = torch.randn(3, 5, 7, 32, device=cuda) * 3.0
+    pl = ops._planes(x)
+    assert pl.dtype == torch.bfloat16 and tuple(pl.shape) == (2, 3, 5, 7, 32)
+    hi = x.to(torch.bfloat16)
+    assert torch.equal(pl[0], hi)                                                   # round-to-nearest-even, like torch
+    assert torch.equal(pl[1], (x - hi.float()).to(torch.bfloat16))
+    rec = pl[0].float() + pl[1].float()
+    assert float(((rec - x).abs() / x.abs().clamp_min(1e-30)).max()) < 2.0 ** -16
+    assert ops._planes(x) is pl                                                     # cached under the version counter
+    x.add_(1.0)
+    assert ops._planes(x) is not pl
+
+
+@pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", CASES)
+@pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
+def test_bf16x3_conv_matches_exact_fp32(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transposed):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Hs + Ci + mode + 5)
+    Hi, Wi = (Hs, Ws) if mode != 1 else (2 * Hs + 1, 2 * Ws + 1)
+    x = torch.randn(B, Hi, Wi, Ci, device=cuda, generator=g)
+    wshape = (k * k, Ci, Co) if transposed else (k * k, Co, Ci)
+    w = torch.randn(*wshape, device=cuda, generator=g) / math.sqrt(Ci * k * k)
+    y_x3 = run(x, w, k, mode, flip, transposed, 3)
+    y_ref = run(x, w, k, mode, flip, transposed, 1)
+    torch.cuda.synchronize()
+    e = gu.rel_err(y_x3.cpu().numpy(), y_ref.cpu().numpy())
+    assert 1e-8 < e < 5e-5, e        # > 1e-8: not the SIMT kernel again
+
+
+@pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", WG_CASES)
+@pytest.mark.parametrize("flip,transposed", [(False, False), (True, True)])
+def test_bf16x3_wgrad_matches_exact_fp32(cuda, B, Hs, Ws, Ci, Co, k, mode, flip, transposed):
+    from gif_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 77 + Hs + Ci + mode + 5)
+    if mode == 0:
+        Hi, Wi, Ho, Wo = Hs, Ws, Hs, Ws
+    elif mode == 1:
+        Hi, Wi, Ho, Wo = 2 * Hs + 1, 2 * Ws + 1, Hs, Ws
+    else:
+        Hi, Wi, Ho, Wo = Hs, Ws, 2 * Hs + 1, 2 * Ws + 1
+    x = torch.randn(B, Hi, Wi, Ci, device=cuda, generator=g)
+    gy = torch.randn(B, Ho, Wo, Co, device=cuda, generator=g)
+    res = []
+    for impl in (3, 1):
+        old = ops.CONV_IMPL
+        ops.CONV_IMPL = impl
+        try:
+            assert lib_path(ops, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl) == impl
+            res.append(ops._wgrad_raw(x, gy, k, mode, flip, transposed))
+        finally:
+            ops.CONV_IMPL = old
+    torch.cuda.synchronize()
+    e = gu.rel_err(res[0].cpu().numpy(), res[1].cpu().numpy())
+    assert 1e-8 < e < 5e-5, e
+
+
+def lib_path(ops, B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl):
+    from gif_b200._lib import lib
+    return lib.gifb200_conv2d_wgrad_path(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl)
+
+
+def test_bf16x3_northstar_shape_sampled(cuda):
+    """The north-star layer's contraction (128 -> 128, 3x3, 256^2; B = 4 here): bf16x3 and tf32 against exact fp32."""
+    from gif_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn(4, 256, 256, 128, device=cuda, generator=g)
+    w = torch.randn(9, 128, 128, device=cuda, generator=g) / math.sqrt(1152)
+    y32 = run(x, w, 3, 0, False, False, 1)
+    e3 = gu.rel_err(run(x, w, 3, 0, False, False, 3).cpu().numpy(), y32.cpu().numpy())
+    et = gu.rel_err(run(round_tf32(x), w, 3, 0, False, False, 2).cpu().numpy(), y32.cpu().numpy())
+    print(f"north-star contraction vs exact fp32: bf16x3 {e3:.2e}, tf32 {et:.2e}")
+    assert e3 < 5e-5 and et < 1e-3

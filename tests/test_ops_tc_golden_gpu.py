@@ -1,0 +1,139 @@
+"""GPU parity of the contraction operators AT TENSOR-CORE SHAPES against goldens of the unmodified reference
+(tests/golden/ops_tc.npz, written by oracle/make_tc_golden.py: float64 evaluation of the reference modules + the
+reference's own fp32-vs-fp64 floor), in every precision mode of gif_b200.ops:
+
+    mode      kernel                                       bar, forward      bar, first derivatives
+    tf32      tcgen05 kind::tf32                           1e-3              max(1e-3, 3 x fp32 floor)
+    bf16x3    tcgen05 kind::f16, hi*hi + hi*lo + lo*hi     1e-4              max(1e-4, 3 x fp32 floor)
+    fp32      SIMT fp32                                    2e-5              max(2e-5, 3 x fp32 floor)
+
+The bar of BASELINE.json is 1e-3 relative to fp32; both the max-norm relative error (golden_util.rel_err) and the
+L2-relative error must be inside the bar.  These shapes run on the tensor cores in tf32 / bf16x3 mode (asserted through
+the workspace query of the C ABI)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+MODES = [("tf32", 1e-3), ("bf16x3", 1e-4), ("fp32", 2e-5)]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return gu.load_golden("ops_tc.npz")
+
+
+def _err(got, ref_full_or_sample, g, key, sampled):
+    if sampled:
+        s, _ = gu.sample(got, len(ref_full_or_sample), 9)
+        ref = ref_full_or_sample
+        emax = float(np.abs(s - ref).max() / float(g[key + "_absmax"]))
+        el2 = float(np.linalg.norm(s - ref) / np.linalg.norm(ref))
+    else:
+        a = got.detach().double().cpu().numpy()
+        emax = gu.rel_err(a, ref_full_or_sample)
+        el2 = float(np.linalg.norm(a - ref_full_or_sample) / np.linalg.norm(ref_full_or_sample))
+    return emax, el2
+
+
+def _check(tag, names, tensors, g, tol, report):
+    for n, t in zip(names, tensors):
+        key = f"{tag}_{n}"
+        sampled = (key + "_absmax") in g.files
+        emax, el2 = _err(t, g[key], g, key, sampled)
+        bar = tol if n == "y" else max(tol, 3 * float(g[key + "_floor"]))
+        report.append(f"{n} {max(emax, el2):.1e}/{bar:.0e}")
+        assert emax < bar and el2 < bar, f"{tag}.{n}: max-norm rel {emax:.2e}, L2 rel {el2:.2e} >= {bar:.1e}"
+
+
+def _assert_tensor_core(B, H, W, ci, co, k, mode_id=0):
+    from gif_b200._lib import lib
+    ho = H if mode_id == 0 else ((H - k) // 2 + 1 if mode_id == 1 else 2 * (H - 1) + k)
+    assert lib.gifb200_conv2d_workspace_bytes(B, H, W, ci, ho, ho, co, k, mode_id, 0, 2) > 0, "shape not on the tcgen05 path"
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+@pytest.mark.parametrize("tag,ci,co,k,demod,up,b,hw", [
+    ("mc_plain", 64, 64, 3, True, False, 3, 16), ("mc_up", 64, 32, 3, True, True, 3, 8), ("mc_rgb", 64, 3, 1, False, False, 3, 16),
+    ("mc_northstar", 128, 128, 3, True, False, 2, 256), ("mc_config1", 512, 512, 3, True, False, 4, 64)])
+def test_modulated_conv_tc_shapes(cuda, gold, mode, tol, tag, ci, co, k, demod, up, b, hw):
+    """ModulatedConv2d (cl.py:307-349): plain / upsample / ToRGB, the north-star layer (128 -> 128 @256^2) and BASELINE
+    configs[0] (512 -> 512 @64^2, bs4): output and all five first derivatives."""
+    from gif_b200 import ops
+    from gif_b200.model import stylegan2_common_layers as cl
+    ops.set_precision(mode)
+    try:
+        if k == 3:
+            _assert_tensor_core(b, hw, hw, ci, co, 3, 2 if up else 0)
+        m = cl.ModulatedConv2d(ci, co, k, 512, demodulate=demod, upsample=up).to(cuda)
+        m.weight.data = gu.randn((1, co, ci, k, k), 120).to(cuda)
+        m.modulation.weight.data = gu.randn((ci, 512), 121).to(cuda)
+        m.modulation.bias.data = (1.0 + 0.1 * gu.randn((ci,), 122)).to(cuda)
+        x = gu.randn((b, ci, hw, hw), 123).to(cuda).requires_grad_(True)
+        st = gu.randn((b, 512), 124).to(cuda).requires_grad_(True)
+        y = m(x, st)
+        gy = gu.randn(tuple(y.shape), 125).to(cuda)
+        grads = torch.autograd.grad((y * gy).sum(), [x, st, m.weight, m.modulation.weight, m.modulation.bias])
+        rep = []
+        _check(tag, "y gx gstyle gw gmodw gmodb".split(), [y] + list(grads), gold, tol, rep)
+        print(f"{tag} [{mode}]: " + "  ".join(rep))
+    finally:
+        ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+@pytest.mark.parametrize("tag,ci,co,k,stride,pad,b,hw", [("ec_s1", 64, 128, 3, 1, 1, 2, 32), ("ec_s2", 64, 64, 3, 2, 0, 2, 33),
+                                                         ("ec_1x1", 64, 32, 1, 1, 0, 2, 32)])
+def test_equal_conv2d_tc_shapes(cuda, gold, mode, tol, tag, ci, co, k, stride, pad, b, hw):
+    """EqualConv2d (cl.py:155-184): stride 1, stride 2, 1x1; output, dgrad, wgrad, bias gradient."""
+    from gif_b200 import ops
+    from gif_b200.model import stylegan2_common_layers as cl
+    ops.set_precision(mode)
+    try:
+        m = cl.EqualConv2d(ci, co, k, stride=stride, padding=pad, bias=True).to(cuda)
+        m.weight.data = gu.randn((co, ci, k, k), 130).to(cuda)
+        m.bias.data = (0.1 * gu.randn((co,), 131)).to(cuda)
+        x = gu.randn((b, ci, hw, hw), 132).to(cuda).requires_grad_(True)
+        y = m(x)
+        gy = gu.randn(tuple(y.shape), 133).to(cuda)
+        grads = torch.autograd.grad((y * gy).sum(), [x, m.weight, m.bias])
+        rep = []
+        _check(tag, "y gx gw gb".split(), [y] + list(grads), gold, tol, rep)
+        print(f"{tag} [{mode}]: " + "  ".join(rep))
+    finally:
+        ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_res_block_tc_shapes(cuda, gold, mode, tol):
+    """ResBlock / ConvLayer (cl.py:752-820) 64 -> 128 at 32^2: fused conv + bias + leaky-ReLU epilogues, blur + stride-2
+    convolutions, the 1x1 skip, the residual merge; output and first derivatives (two chained contractions: the forward
+    bar is 2x the operator bar)."""
+    from gif_b200 import ops
+    from gif_b200.model import stylegan2_common_layers as cl
+    ops.set_precision(mode)
+    try:
+        m = cl.ResBlock(64, 128).to(cuda)
+        sd = m.state_dict()
+        gen = torch.Generator().manual_seed(140)
+        for kk in sd:
+            if kk.endswith("kernel"):
+                continue
+            sd[kk] = torch.randn(sd[kk].shape, generator=gen) * (0.1 if "bias" in kk else 1.0)
+        m.load_state_dict(sd)
+        x = gu.randn((2, 64, 32, 32), 141).to(cuda).requires_grad_(True)
+        y = m(x)
+        gy = gu.randn(tuple(y.shape), 142).to(cuda)
+        named = dict(m.named_parameters())
+        pn = ["conv1.0.weight", "conv1.1.bias", "conv2.1.weight", "conv2.2.bias", "skip.1.weight"]
+        grads = torch.autograd.grad((y * gy).sum(), [x] + [named[n] for n in pn])
+        rep = []
+        _check("rb", ["y", "gx"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep)
+        print(f"rb [{mode}]: " + "  ".join(rep))
+    finally:
+        ops.set_precision("tf32")
