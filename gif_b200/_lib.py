@@ -47,6 +47,8 @@ SIGNATURES = {
     "gifb200_cond_down": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "gifb200_rasterize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "gifb200_rasterize_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _sz, _p]),
+    "gifb200_rasterize_fwd_ex": (_i, [_p] * 7 + [_i] * 5 + [_p, _sz, _p]),
+    "gifb200_rasterize_bwd_ex": (_i, [_p] * 11 + [_i] * 5 + [_p]),
     "gifb200_render_shade": (_i, [_p] * 9 + [_i] * 5 + [_p]),
     "gifb200_rasterize_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "gifb200_flame_lbs_workspace_bytes": (_sz, [_i, _i]),

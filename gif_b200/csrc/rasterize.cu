@@ -1,28 +1,54 @@
-// Deterministic tile-binned z-buffer rasteriser (forward) + barycentric backward.
+// Deterministic tile-binned z-buffer rasteriser (forward) + per-face gather backward, two conventions.
 //
 // The reference (standard_rasterize_cuda_kernel.cu:112-233) runs one thread per triangle, resolves depth with a
 // global-memory CAS loop per covered pixel, writes the winner's payload through uncoalesced scattered stores, and
 // launches the whole kernel twice to paper over the write-after-atomicMin race.  Here:
-//   1. bin_count / bin_scan / bin_fill: every front-facing triangle with a non-empty clamped bbox is appended to the
-//      list of each 8x8-pixel bin its bbox touches (counting pass, per-image exclusive scan, fill pass);
-//   2. raster: one warp per 8x4 half-bin, one pixel per lane.  The warp walks its bin's list (all lanes read the same
-//      triangle -> broadcast loads), every lane evaluates the reference's barycentric formula for its own pixel and
-//      keeps the best (zp, face) pair in registers; depth / triangle / payload are then written once, coalesced.
-// No atomics on the outputs, a single pass, and the result is a pure function of the inputs (ties: lowest face index).
-// fp32 arithmetic uses the non-contracting intrinsics (__fmul_rn/__fadd_rn/...) so it is bit-identical to
-// oracle/rasterize_oracle.c built with -ffp-contract=off.
+//   1. bin_kernel<count> / bin_scan / bin_kernel<fill>: every triangle that passes the convention's face test and has a
+//      non-empty clamped bbox is appended to the list of each 16x16-pixel tile its bbox touches;
+//   2. raster_tile_kernel: one CTA per (image, tile).  The tile's depth buffer lives in SHARED memory as 64-bit keys
+//      (order-preserving depth bits << 32 | face index), initialised from the caller's depth buffer.  Threads take
+//      (list entry, row phase) pairs -- 4 lanes per triangle, rows interleaved -- do the per-triangle setup once, walk
+//      only the triangle's bbox inside the tile (the work is the number of bbox pixels, like the reference's per-triangle
+//      threads, not tile pixels x list length), and resolve depth with shared-memory atomicMin on the key: min depth
+//      wins, exact ties are won by the lowest face index, a fragment must be closer than (or tie) the caller's initial
+//      depth -- a pure function of the inputs.  After a barrier one thread per pixel re-evaluates the winner's
+//      barycentrics with the same arithmetic and writes depth / triangle / payload once, coalesced; up to two attribute
+//      sets (e.g. vertex colours AND vertex normals: "texture + normal render") are interpolated in the same pass.
+//   3. raster_bwd_face_kernel: one thread per triangle GATHERS the gradient of the pixels it owns (triangle buffer ==
+//      its index) over its bbox and writes its 9 (+9 per attribute set) outputs once: no atomics, no zero-initialised
+//      accumulator, deterministic summation order.  (Round 1: 6-15 fp32 atomics per covered pixel.)
+//
+// Conventions (template parameter CONV):
+//   0  the in-repo standard_rasterize semantics (kernel.cu:31-34 front faces only, :79-109 barycentric_weight, :133-136
+//      clamped integer bbox, :144 asymmetric inside test, :148 perspective-interpolated depth): pixel-space input, pixel
+//      centres at integer coordinates.  fp32 arithmetic uses the non-contracting intrinsics so it is bit-identical to
+//      oracle/rasterize_oracle.c built with -ffp-contract=off (and to the reference kernels compiled for the host).
+//   1  pytorch3d's rasterize_meshes as the reference calls it (photometric_optimization/renderer.py:35-67: blur_radius 0,
+//      faces_per_pixel 1, perspective_correct False): NDC input (the caller has already negated x, y, renderer.py:55),
+//      +X left / +Y up so pixel (yi, xi) samples NDC (PixToNdc(W-1-xi), PixToNdc(H-1-yi)) with PixToNdc(i, S) =
+//      -1 + (2 i + 1) / S, edge-function barycentrics over (area + 1e-8), no back-face culling, faces with zmax < 0 or
+//      |area| <= 1e-8 skipped, strictly-inside test (all three > 0), linear depth pz = sum w_i z_i >= 0, min depth wins.
+//      The fork the reference pins is absent and unversioned (requirements.txt:36): PARITY UNPINNED; the checker is the
+//      restatement of these published rules in oracle/rasterize_oracle.c.
 #include "common.cuh"
 
 namespace gifb200 {
 
-constexpr int BIN = 8;
+constexpr int TILE = 16;
+constexpr int SUB = 4;                // lanes per triangle in the tile kernel (bbox rows interleaved)
+constexpr int kNoFace = 0x7fffffff;
+constexpr float kP3dEps = 1e-8f;
 
 struct RasterGeom {
     int B, F, h, w, bins_x, bins_y, nbins;  // nbins per image
 };
 
-__device__ __forceinline__ bool tri_setup(const float* __restrict__ fc, int w, int h, int& xmin, int& xmax, int& ymin,
-                                          int& ymax) {
+// ---------------------------------------------------------------------------------------------- convention 0
+struct Setup0 {
+    float x0, y0, v0x, v0y, v1x, v1y, d00, d01, d11, inv, z0, z1, z2;
+};
+
+__device__ __forceinline__ bool bbox0(const float* __restrict__ fc, int w, int h, int& xmin, int& xmax, int& ymin, int& ymax) {
     const float x0 = fc[0], y0 = fc[1], x1 = fc[3], y1 = fc[4], x2 = fc[6], y2 = fc[7];
     // check_face_frontside (:32-34), separately rounded products
     const bool front = __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(x1, x0)) < __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x2, x0));
@@ -33,8 +59,100 @@ __device__ __forceinline__ bool tri_setup(const float* __restrict__ fc, int w, i
     return front && xmin <= xmax && ymin <= ymax;
 }
 
+__device__ __forceinline__ Setup0 setup0(const float* __restrict__ fc) {
+    Setup0 s;
+    const float x0 = fc[0], y0 = fc[1], x1 = fc[3], y1 = fc[4], x2 = fc[6], y2 = fc[7];
+    s.x0 = x0; s.y0 = y0;
+    s.v0x = __fsub_rn(x2, x0); s.v0y = __fsub_rn(y2, y0);
+    s.v1x = __fsub_rn(x1, x0); s.v1y = __fsub_rn(y1, y0);
+    s.d00 = __fadd_rn(__fmul_rn(s.v0x, s.v0x), __fmul_rn(s.v0y, s.v0y));
+    s.d01 = __fadd_rn(__fmul_rn(s.v0x, s.v1x), __fmul_rn(s.v0y, s.v1y));
+    s.d11 = __fadd_rn(__fmul_rn(s.v1x, s.v1x), __fmul_rn(s.v1y, s.v1y));
+    const float den = __fsub_rn(__fmul_rn(s.d00, s.d11), __fmul_rn(s.d01, s.d01));
+    s.inv = (den == 0.f) ? 0.f : __fdiv_rn(1.f, den);
+    s.z0 = fc[2]; s.z1 = fc[5]; s.z2 = fc[8];
+    return s;
+}
+
+// barycentric_weight (:79-109) + inside test (:144) + depth (:148) for pixel (px,py); no contraction.
+__device__ __forceinline__ bool eval0(const Setup0& s, int px, int py, float& w0, float& w1, float& w2, float& zp) {
+    const float v2x = __fsub_rn(static_cast<float>(px), s.x0), v2y = __fsub_rn(static_cast<float>(py), s.y0);
+    const float d02 = __fadd_rn(__fmul_rn(s.v0x, v2x), __fmul_rn(s.v0y, v2y));
+    const float d12 = __fadd_rn(__fmul_rn(s.v1x, v2x), __fmul_rn(s.v1y, v2y));
+    const float u = __fmul_rn(__fsub_rn(__fmul_rn(s.d11, d02), __fmul_rn(s.d01, d12)), s.inv);
+    const float v = __fmul_rn(__fsub_rn(__fmul_rn(s.d00, d12), __fmul_rn(s.d01, d02)), s.inv);
+    w0 = __fsub_rn(__fsub_rn(1.f, u), v);
+    w1 = v;
+    w2 = u;
+    if (!(w2 >= 0.f && w1 >= 0.f && w0 > 0.f)) return false;
+    const float t = __fadd_rn(__fadd_rn(__fdiv_rn(w0, s.z0), __fdiv_rn(w1, s.z1)), __fdiv_rn(w2, s.z2));
+    zp = __double2float_rn(__ddiv_rn(1.0, static_cast<double>(t)));   // '1.' is a double literal in the reference
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- convention 1 (pytorch3d)
+struct Setup1 {
+    float x0, y0, z0, x1, y1, z1, x2, y2, z2, area, bx0, bx1, by0, by1;
+};
+
+__device__ __forceinline__ float pix_to_ndc(int i, int S) {   // -1 + (2 * i + 1.0f) / S
+    return __fadd_rn(-1.f, __fdiv_rn(__fadd_rn(static_cast<float>(2 * i), 1.0f), static_cast<float>(S)));
+}
+// EdgeFunctionForward(p, v0, v1) = (p.x - v0.x) * (v1.y - v0.y) - (p.y - v0.y) * (v1.x - v0.x)
+__device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
+    return __fsub_rn(__fmul_rn(__fsub_rn(px, ax), __fsub_rn(by, ay)), __fmul_rn(__fsub_rn(py, ay), __fsub_rn(bx, ax)));
+}
+
+// conservative pixel bbox of the NDC bbox (the exact float bbox test is part of eval1)
+__device__ __forceinline__ bool bbox1(const float* __restrict__ fc, int w, int h, int& xmin, int& xmax, int& ymin, int& ymax) {
+    const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
+    if (fmaxf(z0, fmaxf(z1, z2)) < 0.f) return false;                       // face behind the camera
+    const float area = edge_fn(x0, y0, x1, y1, x2, y2);                      // EdgeFunctionForward(v0, v1, v2)
+    if (area <= kP3dEps && area >= -kP3dEps) return false;                   // zero_face_area
+    const float fx0 = fminf(x0, fminf(x1, x2)), fx1 = fmaxf(x0, fmaxf(x1, x2));
+    const float fy0 = fminf(y0, fminf(y1, y2)), fy1 = fmaxf(y0, fmaxf(y1, y2));
+    if (!(fx0 <= fx1 && fy0 <= fy1)) return false;                           // NaN vertices
+    // column j = W-1-xi has ndc = -1 + (2j+1)/W  <=>  j = ((ndc+1) W - 1) / 2
+    const float jx0 = floorf((fx0 + 1.f) * w * 0.5f - 0.5f) - 1.f, jx1 = ceilf((fx1 + 1.f) * w * 0.5f - 0.5f) + 1.f;
+    const float jy0 = floorf((fy0 + 1.f) * h * 0.5f - 0.5f) - 1.f, jy1 = ceilf((fy1 + 1.f) * h * 0.5f - 0.5f) + 1.f;
+    const int ja = static_cast<int>(fmaxf(jx0, 0.f)), jb = static_cast<int>(fminf(jx1, static_cast<float>(w - 1)));
+    const int ka = static_cast<int>(fmaxf(jy0, 0.f)), kb = static_cast<int>(fminf(jy1, static_cast<float>(h - 1)));
+    if (jx1 < 0.f || jy1 < 0.f || jx0 > static_cast<float>(w - 1) || jy0 > static_cast<float>(h - 1)) return false;
+    xmin = w - 1 - jb; xmax = w - 1 - ja; ymin = h - 1 - kb; ymax = h - 1 - ka;
+    return xmin <= xmax && ymin <= ymax;
+}
+
+__device__ __forceinline__ Setup1 setup1(const float* __restrict__ fc) {
+    Setup1 s;
+    s.x0 = fc[0]; s.y0 = fc[1]; s.z0 = fc[2]; s.x1 = fc[3]; s.y1 = fc[4]; s.z1 = fc[5]; s.x2 = fc[6]; s.y2 = fc[7]; s.z2 = fc[8];
+    s.area = __fadd_rn(edge_fn(s.x2, s.y2, s.x0, s.y0, s.x1, s.y1), kP3dEps);     // BarycentricCoordsForward: area + kEpsilon
+    s.bx0 = fminf(s.x0, fminf(s.x1, s.x2)); s.bx1 = fmaxf(s.x0, fmaxf(s.x1, s.x2));
+    s.by0 = fminf(s.y0, fminf(s.y1, s.y2)); s.by1 = fmaxf(s.y0, fmaxf(s.y1, s.y2));
+    return s;
+}
+
+__device__ __forceinline__ bool eval1(const Setup1& s, int px, int py, int w, int h, float& w0, float& w1, float& w2, float& zp) {
+    const float xf = pix_to_ndc(w - 1 - px, w), yf = pix_to_ndc(h - 1 - py, h);
+    if (xf > s.bx1 || xf < s.bx0 || yf > s.by1 || yf < s.by0) return false;     // CheckPointOutsideBoundingBox, blur 0
+    w0 = __fdiv_rn(edge_fn(xf, yf, s.x1, s.y1, s.x2, s.y2), s.area);
+    w1 = __fdiv_rn(edge_fn(xf, yf, s.x2, s.y2, s.x0, s.y0), s.area);
+    w2 = __fdiv_rn(edge_fn(xf, yf, s.x0, s.y0, s.x1, s.y1), s.area);
+    const float pz = __fadd_rn(__fadd_rn(__fmul_rn(w0, s.z0), __fmul_rn(w1, s.z1)), __fmul_rn(w2, s.z2));
+    if (pz < 0.f) return false;                                                  // behind the image plane
+    if (!(w0 > 0.f && w1 > 0.f && w2 > 0.f)) return false;                       // blur_radius 0: strictly inside
+    zp = pz;
+    return true;
+}
+
+template <int CONV>
+__device__ __forceinline__ bool tri_bbox(const float* __restrict__ fc, int w, int h, int& xmin, int& xmax, int& ymin, int& ymax) {
+    if (CONV == 0) return bbox0(fc, w, h, xmin, xmax, ymin, ymax);
+    return bbox1(fc, w, h, xmin, xmax, ymin, ymax);
+}
+
+// ---------------------------------------------------------------------------------------------- binning
 // pass 1 (fill == 0): count[b][bin] += 1 ; pass 2 (fill == 1): list[offset[b][bin] + cursor++] = f
-template <int FILL>
+template <int FILL, int CONV>
 __global__ void __launch_bounds__(256) bin_kernel(const float* __restrict__ fv, RasterGeom g, int* __restrict__ count,
                                                   const int* __restrict__ offset, int* __restrict__ list,
                                                   int capacity, int* __restrict__ overflow) {
@@ -42,8 +160,8 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* __restrict__ fv, 
     if (i >= static_cast<long long>(g.B) * g.F) return;
     const int b = static_cast<int>(i / g.F), f = static_cast<int>(i % g.F);
     int xmin, xmax, ymin, ymax;
-    if (!tri_setup(fv + i * 9, g.w, g.h, xmin, xmax, ymin, ymax)) return;
-    const int bx0 = xmin / BIN, bx1 = xmax / BIN, by0 = ymin / BIN, by1 = ymax / BIN;
+    if (!tri_bbox<CONV>(fv + i * 9, g.w, g.h, xmin, xmax, ymin, ymax)) return;
+    const int bx0 = xmin / TILE, bx1 = xmax / TILE, by0 = ymin / TILE, by1 = ymax / TILE;
     for (int by = by0; by <= by1; ++by)
         for (int bx = bx0; bx <= bx1; ++bx) {
             const int bin = b * g.nbins + by * g.bins_x + bx;
@@ -58,8 +176,8 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* __restrict__ fv, 
 }
 
 // exclusive scan of one image's bin counts (n = bins per image) -- one 1024-thread CTA per image; image b's lists
-// live in list[b*capacity, (b+1)*capacity).  The pass also saves the totals in `total` and re-zeroes `count`, which
-// becomes the fill cursor and, after the fill pass, the list length again.
+// live in list[b*capacity, (b+1)*capacity).  The pass also re-zeroes `count`, which becomes the fill cursor and, after the
+// fill pass, the list length again.
 __global__ void __launch_bounds__(1024) bin_scan_kernel(int* __restrict__ count, int* __restrict__ offset, int n,
                                                         int capacity, int* __restrict__ overflow) {
     __shared__ int warp_tot[32];
@@ -101,114 +219,114 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int* __restrict__ count,
     if (threadIdx.x == 0 && carry > (static_cast<int>(blockIdx.x) + 1) * capacity) overflow[blockIdx.x] = 1;
 }
 
-struct Frag {
-    float zp;
-    int f;
-    float w0, w1, w2;
-};
-
-// barycentric_weight (:79-109) + inside test (:144) + depth (:148) for pixel (px,py); no contraction.
-__device__ __forceinline__ bool shade(const float* __restrict__ fc, float px, float py, float& w0, float& w1, float& w2,
-                                      float& zp) {
-    const float x0 = fc[0], y0 = fc[1], x1 = fc[3], y1 = fc[4], x2 = fc[6], y2 = fc[7];
-    const float v0x = __fsub_rn(x2, x0), v0y = __fsub_rn(y2, y0);
-    const float v1x = __fsub_rn(x1, x0), v1y = __fsub_rn(y1, y0);
-    const float v2x = __fsub_rn(px, x0), v2y = __fsub_rn(py, y0);
-    const float d00 = __fadd_rn(__fmul_rn(v0x, v0x), __fmul_rn(v0y, v0y));
-    const float d01 = __fadd_rn(__fmul_rn(v0x, v1x), __fmul_rn(v0y, v1y));
-    const float d02 = __fadd_rn(__fmul_rn(v0x, v2x), __fmul_rn(v0y, v2y));
-    const float d11 = __fadd_rn(__fmul_rn(v1x, v1x), __fmul_rn(v1y, v1y));
-    const float d12 = __fadd_rn(__fmul_rn(v1x, v2x), __fmul_rn(v1y, v2y));
-    const float den = __fsub_rn(__fmul_rn(d00, d11), __fmul_rn(d01, d01));
-    const float inv = (den == 0.f) ? 0.f : __fdiv_rn(1.f, den);
-    const float u = __fmul_rn(__fsub_rn(__fmul_rn(d11, d02), __fmul_rn(d01, d12)), inv);
-    const float v = __fmul_rn(__fsub_rn(__fmul_rn(d00, d12), __fmul_rn(d01, d02)), inv);
-    w0 = __fsub_rn(__fsub_rn(1.f, u), v);
-    w1 = v;
-    w2 = u;
-    if (!(w2 >= 0.f && w1 >= 0.f && w0 > 0.f)) return false;
-    const float s = __fadd_rn(__fadd_rn(__fdiv_rn(w0, fc[2]), __fdiv_rn(w1, fc[5])), __fdiv_rn(w2, fc[8]));
-    zp = __double2float_rn(__ddiv_rn(1.0, static_cast<double>(s)));   // '1.' is a double literal in the reference
-    return true;
+// ---------------------------------------------------------------------------------------------- tile kernel
+// order-preserving float -> uint (IEEE total order on non-NaN values; -0 is canonicalised to +0 by the caller)
+__device__ __forceinline__ unsigned int depth_bits(float z) {
+    const unsigned int u = __float_as_uint(z);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long make_key(float z, int f) {
+    return (static_cast<unsigned long long>(depth_bits(__fadd_rn(z, 0.f))) << 32) | static_cast<unsigned int>(f);
 }
 
-// One warp per 8x4 half-bin.  brute != 0: ignore the lists and walk all F triangles (overflow fallback).
-__global__ void __launch_bounds__(256) raster_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
-                                                     float* __restrict__ depth, int* __restrict__ tri,
-                                                     float* __restrict__ out3, RasterGeom g,
-                                                     const int* __restrict__ count, const int* __restrict__ offset,
-                                                     const int* __restrict__ list, const int* __restrict__ overflow) {
-    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = static_cast<long long>(g.B) * g.nbins * 2;
-    if (warp >= nwarps) return;
-    const int half = static_cast<int>(warp & 1);
-    const long long gbin = warp >> 1;
-    const int b = static_cast<int>(gbin / g.nbins), bin = static_cast<int>(gbin % g.nbins);
-    const int by = bin / g.bins_x, bx = bin % g.bins_x;
-    const int px = bx * BIN + (lane & 7), py = by * BIN + half * 4 + (lane >> 3);
+template <int CONV>
+__device__ __forceinline__ void interpolate3(const float* __restrict__ c, float b0, float b1, float b2, float* __restrict__ o) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)   // :225, left-to-right, no contraction
+        o[k] = __fadd_rn(__fadd_rn(__fmul_rn(b0, c[k]), __fmul_rn(b1, c[3 + k])), __fmul_rn(b2, c[6 + k]));
+}
+
+// One CTA (256 threads) per 16x16 tile.  overflow[b] != 0: this image's lists did not fit -> every CTA of the image walks
+// all F triangles (still exact).
+template <int CONV>
+__global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
+                                                          const float* __restrict__ colors2, float* __restrict__ depth,
+                                                          int* __restrict__ tri, float* __restrict__ out3,
+                                                          float* __restrict__ out3b, RasterGeom g,
+                                                          const int* __restrict__ count, const int* __restrict__ offset,
+                                                          const int* __restrict__ list, const int* __restrict__ overflow) {
+    __shared__ unsigned long long key[TILE * TILE];
+    const int gbin = blockIdx.x;
+    const int b = gbin / g.nbins, bin = gbin - b * g.nbins;
+    const int by = bin / g.bins_x, bx = bin - by * g.bins_x;
+    const int tx0 = bx * TILE, ty0 = by * TILE;
+    const int t = threadIdx.x;
+    const int px = tx0 + (t & (TILE - 1)), py = ty0 + (t >> 4);
     const bool in_img = px < g.w && py < g.h;
     const long long pix = (static_cast<long long>(b) * g.h + py) * g.w + px;
-    float best_z = in_img ? depth[pix] : 0.f;
-    int best_f = 0x7fffffff;
-    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-    const bool brute = overflow[b] != 0;     // this image's lists did not fit: walk all F triangles (still exact)
+    // phase 0: the tile's depth buffer, initialised from the caller's (a fragment must beat or tie it)
+    {
+        unsigned long long k0 = 0ull;                    // out-of-image / NaN depth: nothing can win
+        if (in_img) {
+            const float d0 = depth[pix];
+            if (d0 == d0) k0 = make_key(d0, kNoFace);
+        }
+        key[t] = k0;
+    }
+    __syncthreads();
+    // phase 1: triangles -> fragments -> shared-memory depth test
+    const bool brute = overflow[b] != 0;
     const int n = brute ? g.F : count[gbin];
     const int* lst = list + (brute ? 0 : offset[gbin]);
-    const float fpx = static_cast<float>(px), fpy = static_cast<float>(py);
     const float* fvb = fv + static_cast<long long>(b) * g.F * 9;
-    for (int j = 0; j < n; ++j) {
+    const int sub = t & (SUB - 1);
+    for (int j = t / SUB; j < n; j += 256 / SUB) {
         const int f = brute ? j : lst[j];
         const float* fc = fvb + static_cast<long long>(f) * 9;
-        if (brute) {
-            int a, c, d, e;
-            if (!tri_setup(fc, g.w, g.h, a, c, d, e)) continue;
-            if (px < a || px > c || py < d || py > e) continue;   // the reference only visits bbox pixels
+        int xmin, xmax, ymin, ymax;
+        if (!tri_bbox<CONV>(fc, g.w, g.h, xmin, xmax, ymin, ymax)) continue;
+        const int xa = max(xmin, tx0), xb = min(xmax, tx0 + TILE - 1), ya = max(ymin, ty0), yb = min(ymax, ty0 + TILE - 1);
+        if (xa > xb || ya > yb) continue;
+        if (CONV == 0) {
+            const Setup0 s = setup0(fc);
+            for (int y = ya + sub; y <= yb; y += SUB)
+                for (int x = xa; x <= xb; ++x) {
+                    float w0, w1, w2, zp;
+                    if (!eval0(s, x, y, w0, w1, w2, zp) || !(zp == zp)) continue;
+                    const unsigned long long k = make_key(zp, f);
+                    unsigned long long* slot = &key[(y - ty0) * TILE + (x - tx0)];
+                    if (k < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, k);
+                }
         } else {
-            // the bbox test is part of the reference's semantics (pixels outside the clamped bbox are never visited)
-            const float x0 = fc[0], y0 = fc[1], x1 = fc[3], y1 = fc[4], x2 = fc[6], y2 = fc[7];
-            const int xmin = static_cast<int>(ceilf(fminf(x0, fminf(x1, x2))));
-            const int xmax = static_cast<int>(floorf(fmaxf(x0, fmaxf(x1, x2))));
-            const int ymin = static_cast<int>(ceilf(fminf(y0, fminf(y1, y2))));
-            const int ymax = static_cast<int>(floorf(fmaxf(y0, fmaxf(y1, y2))));
-            if (px < xmin || px > xmax || py < ymin || py > ymax) continue;
-        }
-        float w0, w1, w2, zp;
-        if (!shade(fc, fpx, fpy, w0, w1, w2, zp)) continue;
-        if (zp < best_z || (zp == best_z && f < best_f)) {
-            best_z = zp; best_f = f; b0 = w0; b1 = w1; b2 = w2;
+            const Setup1 s = setup1(fc);
+            for (int y = ya + sub; y <= yb; y += SUB)
+                for (int x = xa; x <= xb; ++x) {
+                    float w0, w1, w2, zp;
+                    if (!eval1(s, x, y, g.w, g.h, w0, w1, w2, zp) || !(zp == zp)) continue;
+                    const unsigned long long k = make_key(zp, f);
+                    unsigned long long* slot = &key[(y - ty0) * TILE + (x - tx0)];
+                    if (k < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, k);
+                }
         }
     }
-    if (in_img && best_f != 0x7fffffff) {
-        depth[pix] = best_z;
-        tri[pix] = best_f;
+    __syncthreads();
+    // phase 2: one pixel per thread -- re-evaluate the winner (same arithmetic, same values) and write once, coalesced
+    if (!in_img) return;
+    const int f = static_cast<int>(static_cast<unsigned int>(key[t] & 0xffffffffull));
+    if (f == kNoFace || key[t] == 0ull) return;
+    const float* fc = fvb + static_cast<long long>(f) * 9;
+    float w0, w1, w2, zp;
+    if (CONV == 0) { const Setup0 s = setup0(fc); eval0(s, px, py, w0, w1, w2, zp); }
+    else { const Setup1 s = setup1(fc); eval1(s, px, py, g.w, g.h, w0, w1, w2, zp); }
+    depth[pix] = zp;
+    tri[pix] = f;
+    if (out3) {
         float* o = out3 + pix * 3;
-        if (colors) {
-            const float* c = colors + (static_cast<long long>(b) * g.F + best_f) * 9;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)   // :225, left-to-right, no contraction
-                o[k] = __fadd_rn(__fadd_rn(__fmul_rn(b0, c[k]), __fmul_rn(b1, c[3 + k])), __fmul_rn(b2, c[6 + k]));
-        } else {
-            o[0] = b0; o[1] = b1; o[2] = b2;
-        }
+        if (colors) interpolate3<CONV>(colors + (static_cast<long long>(b) * g.F + f) * 9, w0, w1, w2, o);
+        else { o[0] = w0; o[1] = w1; o[2] = w2; }
     }
+    if (out3b && colors2) interpolate3<CONV>(colors2 + (static_cast<long long>(b) * g.F + f) * 9, w0, w1, w2, out3b + pix * 3);
 }
 
-// ------------------------------------------------------------------------------------------------ backward
-// One thread per pixel; analytic derivatives of bw = (1-u-v, v, u) (kernel.cu:79-109), of zp (:148) and of the
-// colour interpolation (:225) w.r.t. the owning face's vertices / colours, scatter-added with fp32 atomics.
-__global__ void __launch_bounds__(256) raster_bwd_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
-                                                         const int* __restrict__ tri, const float* __restrict__ g_bary,
-                                                         const float* __restrict__ g_img, const float* __restrict__ g_depth,
-                                                         float* __restrict__ g_fv, float* __restrict__ g_col, int B, int F,
-                                                         int h, int w) {
-    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (pix >= static_cast<long long>(B) * h * w) return;
-    const int f = tri[pix];
-    if (f < 0) return;
-    const int px = static_cast<int>(pix % w), py = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long long>(w) * h));
-    const long long fo = (static_cast<long long>(b) * F + f) * 9;
-    const float* fc = fv + fo;
+// ---------------------------------------------------------------------------------------------- backward
+// Analytic derivatives of the winner's barycentrics / depth / attribute interpolation w.r.t. the face's vertices and
+// attributes, accumulated in registers by the thread that owns the face.
+struct FaceGrad {
+    float fv[9], c1[9], c2[9];
+};
+
+__device__ __forceinline__ void bwd_pixel0(const float* __restrict__ fc, int px, int py, float gw0, float gw1, float gw2, float gz_up,
+                                           bool has_depth, FaceGrad& a, float& w0o, float& w1o, float& w2o) {
     const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
     const float v0x = x2 - x0, v0y = y2 - y0, v1x = x1 - x0, v1y = y1 - y0, v2x = px - x0, v2y = py - y0;
     const float d00 = v0x * v0x + v0y * v0y, d01 = v0x * v1x + v0y * v1y, d02 = v0x * v2x + v0y * v2y;
@@ -218,43 +336,25 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const float* __restrict
     const float nu = d11 * d02 - d01 * d12, nv = d00 * d12 - d01 * d02;
     const float u = nu * inv, v = nv * inv;
     const float w0 = 1.f - u - v, w1 = v, w2 = u;
-    // upstream gradient on (w0,w1,w2)
-    float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
-    if (g_bary) { gw0 += g_bary[pix * 3]; gw1 += g_bary[pix * 3 + 1]; gw2 += g_bary[pix * 3 + 2]; }
-    if (g_img && colors) {
-        const float* c = colors + fo;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float gk = g_img[pix * 3 + k];
-            gw0 += gk * c[k]; gw1 += gk * c[3 + k]; gw2 += gk * c[6 + k];
-            if (g_col) {
-                atomicAdd(g_col + fo + k, gk * w0);
-                atomicAdd(g_col + fo + 3 + k, gk * w1);
-                atomicAdd(g_col + fo + 6 + k, gk * w2);
-            }
-        }
-    }
-    if (g_depth) {
+    w0o = w0; w1o = w1; w2o = w2;
+    if (has_depth) {
         const float s = w0 / z0 + w1 / z1 + w2 / z2;
         const float zp = 1.f / s;
-        const float gz = g_depth[pix] * (-zp * zp);   // d zp / d s
+        const float gz = gz_up * (-zp * zp);   // d zp / d s
         gw0 += gz / z0; gw1 += gz / z1; gw2 += gz / z2;
-        atomicAdd(g_fv + fo + 2, gz * (-w0 / (z0 * z0)));
-        atomicAdd(g_fv + fo + 5, gz * (-w1 / (z1 * z1)));
-        atomicAdd(g_fv + fo + 8, gz * (-w2 / (z2 * z2)));
+        a.fv[2] += gz * (-w0 / (z0 * z0));
+        a.fv[5] += gz * (-w1 / (z1 * z1));
+        a.fv[8] += gz * (-w2 / (z2 * z2));
     }
     // (w0,w1,w2) = (1-u-v, v, u)  ->  gu = gw2 - gw0, gv = gw1 - gw0
     const float gu = gw2 - gw0, gv = gw1 - gw0;
-    // u = nu*inv, v = nv*inv, inv = 1/den
     const float g_nu = gu * inv, g_nv = gv * inv;
     const float g_den = den == 0.f ? 0.f : -(gu * nu + gv * nv) * inv * inv;
-    // nu = d11*d02 - d01*d12 ; nv = d00*d12 - d01*d02 ; den = d00*d11 - d01^2
     const float g_d00 = g_nv * d12 + g_den * d11;
     const float g_d11 = g_nu * d02 + g_den * d00;
     const float g_d01 = -g_nu * d12 - g_nv * d02 - 2.f * g_den * d01;
     const float g_d02 = g_nu * d11 - g_nv * d01;
     const float g_d12 = -g_nu * d01 + g_nv * d00;
-    // dots -> vectors
     const float g_v0x = 2.f * g_d00 * v0x + g_d01 * v1x + g_d02 * v2x;
     const float g_v0y = 2.f * g_d00 * v0y + g_d01 * v1y + g_d02 * v2y;
     const float g_v1x = 2.f * g_d11 * v1x + g_d01 * v0x + g_d12 * v2x;
@@ -262,12 +362,104 @@ __global__ void __launch_bounds__(256) raster_bwd_kernel(const float* __restrict
     const float g_v2x = g_d02 * v0x + g_d12 * v1x;
     const float g_v2y = g_d02 * v0y + g_d12 * v1y;
     // v0 = p2-p0, v1 = p1-p0, v2 = p-p0
-    atomicAdd(g_fv + fo + 0, -(g_v0x + g_v1x + g_v2x));
-    atomicAdd(g_fv + fo + 1, -(g_v0y + g_v1y + g_v2y));
-    atomicAdd(g_fv + fo + 3, g_v1x);
-    atomicAdd(g_fv + fo + 4, g_v1y);
-    atomicAdd(g_fv + fo + 6, g_v0x);
-    atomicAdd(g_fv + fo + 7, g_v0y);
+    a.fv[0] += -(g_v0x + g_v1x + g_v2x);
+    a.fv[1] += -(g_v0y + g_v1y + g_v2y);
+    a.fv[3] += g_v1x;
+    a.fv[4] += g_v1y;
+    a.fv[6] += g_v0x;
+    a.fv[7] += g_v0y;
+}
+
+// convention 1: w_i = E_i(p) / A with E_0 = E(p,v1,v2), E_1 = E(p,v2,v0), E_2 = E(p,v0,v1), A = E(v2,v0,v1) + eps; pz = sum w_i z_i
+__device__ __forceinline__ void bwd_pixel1(const float* __restrict__ fc, int px, int py, int w, int h, float gw0, float gw1, float gw2,
+                                           float gz_up, bool has_depth, FaceGrad& a, float& w0o, float& w1o, float& w2o) {
+    const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
+    const float xf = -1.f + (2 * (w - 1 - px) + 1.0f) / w, yf = -1.f + (2 * (h - 1 - py) + 1.0f) / h;
+    const float A = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + kP3dEps;
+    const float e0 = (xf - x1) * (y2 - y1) - (yf - y1) * (x2 - x1);
+    const float e1 = (xf - x2) * (y0 - y2) - (yf - y2) * (x0 - x2);
+    const float e2 = (xf - x0) * (y1 - y0) - (yf - y0) * (x1 - x0);
+    const float iA = 1.f / A;
+    const float w0 = e0 * iA, w1 = e1 * iA, w2 = e2 * iA;
+    w0o = w0; w1o = w1; w2o = w2;
+    if (has_depth) {        // pz = w0 z0 + w1 z1 + w2 z2
+        gw0 += gz_up * z0; gw1 += gz_up * z1; gw2 += gz_up * z2;
+        a.fv[2] += gz_up * w0; a.fv[5] += gz_up * w1; a.fv[8] += gz_up * w2;
+    }
+    const float ge0 = gw0 * iA, ge1 = gw1 * iA, ge2 = gw2 * iA;
+    const float gA = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * iA * iA;
+    // E(p,a,b): dE/da = (p.y - b.y, b.x - p.x), dE/db = (-(p.y - a.y), p.x - a.x)
+    // e0 = E(p, v1, v2)
+    a.fv[3] += ge0 * (yf - y2); a.fv[4] += ge0 * (x2 - xf); a.fv[6] += ge0 * -(yf - y1); a.fv[7] += ge0 * (xf - x1);
+    // e1 = E(p, v2, v0)
+    a.fv[6] += ge1 * (yf - y0); a.fv[7] += ge1 * (x0 - xf); a.fv[0] += ge1 * -(yf - y2); a.fv[1] += ge1 * (xf - x2);
+    // e2 = E(p, v0, v1)
+    a.fv[0] += ge2 * (yf - y1); a.fv[1] += ge2 * (x1 - xf); a.fv[3] += ge2 * -(yf - y0); a.fv[4] += ge2 * (xf - x0);
+    // A = E(v2, v0, v1) + eps: "p" = v2, a = v0, b = v1
+    a.fv[6] += gA * (y1 - y0); a.fv[7] += gA * -(x1 - x0);
+    a.fv[0] += gA * (y2 - y1); a.fv[1] += gA * (x1 - x2);
+    a.fv[3] += gA * -(y2 - y0); a.fv[4] += gA * (x2 - x0);
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
+                                                              const float* __restrict__ colors2, const int* __restrict__ tri,
+                                                              const float* __restrict__ g_bary, const float* __restrict__ g_img,
+                                                              const float* __restrict__ g_img2, const float* __restrict__ g_depth,
+                                                              float* __restrict__ g_fv, float* __restrict__ g_col,
+                                                              float* __restrict__ g_col2, int B, int F, int h, int w) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * F) return;
+    const int b = static_cast<int>(i / F), f = static_cast<int>(i - static_cast<long long>(b) * F);
+    const long long fo = i * 9;
+    const float* fc = fv + fo;
+    FaceGrad a;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { a.fv[k] = 0.f; a.c1[k] = 0.f; a.c2[k] = 0.f; }
+    int xmin, xmax, ymin, ymax;
+    if (tri_bbox<CONV>(fc, w, h, xmin, xmax, ymin, ymax)) {
+        const long long img = static_cast<long long>(b) * h * w;
+        for (int y = ymin; y <= ymax; ++y)
+            for (int x = xmin; x <= xmax; ++x) {
+                const long long pix = img + static_cast<long long>(y) * w + x;
+                if (tri[pix] != f) continue;
+                float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
+                if (g_bary) { gw0 = g_bary[pix * 3]; gw1 = g_bary[pix * 3 + 1]; gw2 = g_bary[pix * 3 + 2]; }
+                float gi[3] = {0.f, 0.f, 0.f}, gi2[3] = {0.f, 0.f, 0.f};
+                if (g_img && colors) {
+                    const float* c = colors + fo;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gi[k] = g_img[pix * 3 + k];
+                        gw0 += gi[k] * c[k]; gw1 += gi[k] * c[3 + k]; gw2 += gi[k] * c[6 + k];
+                    }
+                }
+                if (g_img2 && colors2) {
+                    const float* c = colors2 + fo;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        gi2[k] = g_img2[pix * 3 + k];
+                        gw0 += gi2[k] * c[k]; gw1 += gi2[k] * c[3 + k]; gw2 += gi2[k] * c[6 + k];
+                    }
+                }
+                float w0, w1, w2;
+                if (CONV == 0) bwd_pixel0(fc, x, y, gw0, gw1, gw2, g_depth ? g_depth[pix] : 0.f, g_depth != nullptr, a, w0, w1, w2);
+                else bwd_pixel1(fc, x, y, w, h, gw0, gw1, gw2, g_depth ? g_depth[pix] : 0.f, g_depth != nullptr, a, w0, w1, w2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    a.c1[k] += gi[k] * w0; a.c1[3 + k] += gi[k] * w1; a.c1[6 + k] += gi[k] * w2;
+                    a.c2[k] += gi2[k] * w0; a.c2[3 + k] += gi2[k] * w1; a.c2[6 + k] += gi2[k] * w2;
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g_fv[fo + k] = a.fv[k];
+    if (g_col)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_col[fo + k] = a.c1[k];
+    if (g_col2)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g_col2[fo + k] = a.c2[k];
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -277,28 +469,24 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 using namespace gifb200;
 
 // workspace layout: [count: B*nbins ints][offset: B*nbins ints][overflow flags: B ints (padded)][list: B*capacity ints]
-static int list_capacity(int F) {   // list slots per image; a FLAME render at 256^2 needs ~1.2 F, allow 8 F
+static int list_capacity(int F) {   // list slots per image; a FLAME render at 256^2 needs ~1 F at 16x16 tiles, allow 8 F
     const long long cap = static_cast<long long>(F) * 8 + 1024;
     return static_cast<int>(cap > 0x3fffffffLL ? 0x3fffffffLL : cap);
 }
 
 extern "C" size_t gifb200_rasterize_workspace_bytes(int B, int F, int h, int w) {
     if (B <= 0 || h <= 0 || w <= 0 || F < 0) return 0;
-    const size_t nb = static_cast<size_t>(B) * ((h + BIN - 1) / BIN) * ((w + BIN - 1) / BIN);
+    const size_t nb = static_cast<size_t>(B) * ((h + TILE - 1) / TILE) * ((w + TILE - 1) / TILE);
     return align_up(nb * 4, 256) * 2 + align_up(static_cast<size_t>(B) * 4, 256) + static_cast<size_t>(list_capacity(F)) * 4 * B;
 }
 
-extern "C" int gifb200_rasterize_fwd(const float* face_vertices, const float* face_colors, float* depth,
-                                     int32_t* triangle, float* out3, int B, int F, int h, int w, void* workspace,
-                                     size_t workspace_bytes, gifb200_stream_t stream) {
-    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0, GIFB200_E_SHAPE, "rasterize: bad shape");
-    if (B == 0 || F == 0) return GIFB200_OK;     // nothing can be written: buffers keep the caller's initial values
-    GIFB200_REQUIRE(workspace && workspace_bytes >= gifb200_rasterize_workspace_bytes(B, F, h, w), GIFB200_E_WORKSPACE,
-                    "rasterize: workspace too small (see gifb200_rasterize_workspace_bytes)");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+template <int CONV>
+static int rasterize_fwd_impl(const float* face_vertices, const float* face_colors, const float* face_colors2, float* depth,
+                              int32_t* triangle, float* out3, float* out3b, int B, int F, int h, int w, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st) {
     RasterGeom g;
     g.B = B; g.F = F; g.h = h; g.w = w;
-    g.bins_x = (w + BIN - 1) / BIN; g.bins_y = (h + BIN - 1) / BIN; g.nbins = g.bins_x * g.bins_y;
+    g.bins_x = (w + TILE - 1) / TILE; g.bins_y = (h + TILE - 1) / TILE; g.nbins = g.bins_x * g.bins_y;
     const size_t nb = static_cast<size_t>(B) * g.nbins;
     GIFB200_REQUIRE(nb < 0x7fffffffULL / 64, GIFB200_E_SHAPE, "rasterize: too many bins");
     char* ws = static_cast<char*>(workspace);
@@ -311,16 +499,60 @@ extern "C" int gifb200_rasterize_fwd(const float* face_vertices, const float* fa
     cudaError_t e = cudaMemsetAsync(ws, 0, align_up(nb * 4, 256) * 2 + align_up(static_cast<size_t>(B) * 4, 256), st);
     if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "rasterize memset", cudaGetErrorString(e));
     const long long ntri = static_cast<long long>(B) * F;
-    bin_kernel<0><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);
+    bin_kernel<0, CONV><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);
     GIFB200_LAUNCH_CHECK("bin_kernel<count>");
     bin_scan_kernel<<<B, 1024, 0, st>>>(count, offset, g.nbins, capacity, overflow);
     GIFB200_LAUNCH_CHECK("bin_scan_kernel");
-    bin_kernel<1><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);
+    bin_kernel<1, CONV><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);
     GIFB200_LAUNCH_CHECK("bin_kernel<fill>");
-    const long long nwarps = static_cast<long long>(nb) * 2;
-    raster_kernel<<<cdiv(nwarps * 32, 256), 256, 0, st>>>(face_vertices, face_colors, depth, triangle, out3, g, count,
-                                                          offset, list, overflow);
-    GIFB200_LAUNCH_CHECK("raster_kernel");
+    raster_tile_kernel<CONV><<<static_cast<unsigned int>(nb), 256, 0, st>>>(face_vertices, face_colors, face_colors2, depth,
+                                                                            triangle, out3, out3b, g, count, offset, list, overflow);
+    GIFB200_LAUNCH_CHECK("raster_tile_kernel");
+    return GIFB200_OK;
+}
+
+extern "C" int gifb200_rasterize_fwd_ex(const float* face_vertices, const float* face_colors, const float* face_colors2,
+                                        float* depth, int32_t* triangle, float* out3, float* out3b, int B, int F, int h, int w,
+                                        int convention, void* workspace, size_t workspace_bytes, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0, GIFB200_E_SHAPE, "rasterize: bad shape");
+    GIFB200_REQUIRE(convention == 0 || convention == 1, GIFB200_E_SHAPE, "rasterize: convention must be 0 (standard_rasterize) or 1 (pytorch3d)");
+    GIFB200_REQUIRE(!face_colors2 || (face_colors && out3b), GIFB200_E_SHAPE, "rasterize: a second attribute set needs the first one and out3b");
+    if (B == 0 || F == 0) return GIFB200_OK;     // nothing can be written: buffers keep the caller's initial values
+    GIFB200_REQUIRE(workspace && workspace_bytes >= gifb200_rasterize_workspace_bytes(B, F, h, w), GIFB200_E_WORKSPACE,
+                    "rasterize: workspace too small (see gifb200_rasterize_workspace_bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (convention == 0)
+        return rasterize_fwd_impl<0>(face_vertices, face_colors, face_colors2, depth, triangle, out3, out3b, B, F, h, w, workspace, workspace_bytes, st);
+    return rasterize_fwd_impl<1>(face_vertices, face_colors, face_colors2, depth, triangle, out3, out3b, B, F, h, w, workspace, workspace_bytes, st);
+}
+
+extern "C" int gifb200_rasterize_fwd(const float* face_vertices, const float* face_colors, float* depth,
+                                     int32_t* triangle, float* out3, int B, int F, int h, int w, void* workspace,
+                                     size_t workspace_bytes, gifb200_stream_t stream) {
+    return gifb200_rasterize_fwd_ex(face_vertices, face_colors, nullptr, depth, triangle, out3, nullptr, B, F, h, w, 0, workspace,
+                                    workspace_bytes, stream);
+}
+
+extern "C" int gifb200_rasterize_bwd_ex(const float* face_vertices, const float* face_colors, const float* face_colors2,
+                                        const int32_t* triangle, const float* g_bary, const float* g_img, const float* g_img2,
+                                        const float* g_depth, float* g_face_vertices, float* g_face_colors,
+                                        float* g_face_colors2, int B, int F, int h, int w, int convention,
+                                        gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0, GIFB200_E_SHAPE, "rasterize_bwd: bad shape");
+    GIFB200_REQUIRE(convention == 0 || convention == 1, GIFB200_E_SHAPE, "rasterize_bwd: convention must be 0 or 1");
+    GIFB200_REQUIRE(g_face_vertices != nullptr, GIFB200_E_SHAPE, "rasterize_bwd: g_face_vertices is required");
+    GIFB200_REQUIRE(!g_img || face_colors, GIFB200_E_SHAPE, "rasterize_bwd: g_img needs face_colors");
+    GIFB200_REQUIRE(!g_img2 || face_colors2, GIFB200_E_SHAPE, "rasterize_bwd: g_img2 needs face_colors2");
+    if (B == 0 || F == 0) return GIFB200_OK;
+    const long long ntri = static_cast<long long>(B) * F;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (convention == 0)
+        raster_bwd_face_kernel<0><<<cdiv(ntri, 128), 128, 0, st>>>(face_vertices, face_colors, face_colors2, triangle, g_bary, g_img,
+                                                                  g_img2, g_depth, g_face_vertices, g_face_colors, g_face_colors2, B, F, h, w);
+    else
+        raster_bwd_face_kernel<1><<<cdiv(ntri, 128), 128, 0, st>>>(face_vertices, face_colors, face_colors2, triangle, g_bary, g_img,
+                                                                  g_img2, g_depth, g_face_vertices, g_face_colors, g_face_colors2, B, F, h, w);
+    GIFB200_LAUNCH_CHECK("raster_bwd_face_kernel");
     return GIFB200_OK;
 }
 
@@ -328,13 +560,6 @@ extern "C" int gifb200_rasterize_bwd(const float* face_vertices, const float* fa
                                      const float* g_bary, const float* g_img, const float* g_depth,
                                      float* g_face_vertices, float* g_face_colors, int B, int F, int h, int w,
                                      gifb200_stream_t stream) {
-    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0, GIFB200_E_SHAPE, "rasterize_bwd: bad shape");
-    GIFB200_REQUIRE(g_face_vertices != nullptr, GIFB200_E_SHAPE, "rasterize_bwd: g_face_vertices is required");
-    GIFB200_REQUIRE(!g_img || face_colors, GIFB200_E_SHAPE, "rasterize_bwd: g_img needs face_colors");
-    if (B == 0 || F == 0) return GIFB200_OK;
-    const long long npix = static_cast<long long>(B) * h * w;
-    raster_bwd_kernel<<<cdiv(npix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        face_vertices, face_colors, triangle, g_bary, g_img, g_depth, g_face_vertices, g_face_colors, B, F, h, w);
-    GIFB200_LAUNCH_CHECK("raster_bwd_kernel");
-    return GIFB200_OK;
+    return gifb200_rasterize_bwd_ex(face_vertices, face_colors, nullptr, triangle, g_bary, g_img, nullptr, g_depth, g_face_vertices,
+                                    g_face_colors, nullptr, B, F, h, w, 0, stream);
 }

@@ -6,11 +6,17 @@ Follows the arithmetic of the reference's render path
     Renderer.forward / add_SHlight / render_normal  (my_utils/photometric_optimization/renderer.py:130-221,291-305)
     util.vertex_normals / face_vertices / batch_orth_proj (my_utils/photometric_optimization/util.py:73-83,135-189)
     OverLayViz.get_rendered_mesh quantisation       (my_utils/visualize_flame_overlay.py:29-31)
-with ONE difference that is stated, not hidden: the reference rasterises with the third-party pytorch3d
-``rasterize_meshes`` (an unpinned fork, absent from the tree; SURVEY 8c: "parity unpinned"), this module rasterises with
-the in-repo ``standard_rasterize`` semantics (gif_b200.rasterize: pixel centres at integer coordinates after the
-visibility.py:38-40 mapping, front faces only, perspective-interpolated depth, ties -> lowest face index).  Everything
-downstream of the (triangle, bary) buffers is the reference's formulae, fused into one kernel (gifb200_render_shade).
+Two rasterisation conventions (``FlameRenderer(..., convention=...)``), the choice stated, not hidden:
+  "pytorch3d" (default) -- what the reference's conditioning maps are actually made with: pytorch3d ``rasterize_meshes`` as
+               ``Pytorch3dRasterizer.forward`` calls it (renderer.py:46-67: NDC with x, y negated, pixel centres at +0.5,
+               no back-face culling, linear depth, strictly-inside test), gifb200_rasterize_fwd_ex convention 1.  The fork the
+               reference pins is absent and unversioned: PARITY UNPINNED, checked against the restatement of
+               the published rules in oracle/rasterize_oracle.c;
+  "standard"  -- the in-repo ``standard_rasterize`` semantics (gif_b200.rasterize: pixel centres at integer coordinates
+               after the visibility.py:38-40 mapping, front faces only, perspective-interpolated depth), bit-exact against
+               the reference's own kernels.
+Everything downstream of the (triangle, bary) buffers is the reference's formulae, fused into one kernel
+(gifb200_render_shade).
 
 Conditioning maps are *data* for the GAN (the reference detaches every attribute, renderer.py:149-150), so this path is
 forward-only; the differentiable rasteriser itself is gif_b200.rasterize.rasterize.
@@ -49,8 +55,11 @@ def vertex_normals(vertices, faces):
 class FlameRenderer(torch.nn.Module):
     """Renderer (renderer.py:87-127) for a fixed topology: faces (F,3), per-corner UVs from (uvcoords (Vt,2), uvfaces (F,3))."""
 
-    def __init__(self, faces, uvcoords, uvfaces, image_size=256):
+    def __init__(self, faces, uvcoords, uvfaces, image_size=256, convention="pytorch3d"):
         super().__init__()
+        if convention not in rasterize.CONVENTIONS:
+            raise ValueError(f"convention must be one of {sorted(rasterize.CONVENTIONS)}")
+        self.convention = convention
         self.image_size = image_size
         self.register_buffer("faces", faces.long())
         uv = torch.cat([uvcoords, torch.ones_like(uvcoords[:, :1])], -1) * 2 - 1       # renderer.py:107-109
@@ -66,17 +75,22 @@ class FlameRenderer(torch.nn.Module):
         H = W = self.image_size
         tv = transformed_vertices.clone().float()
         tv[:, :, 2] = tv[:, :, 2] + 10                                             # renderer.py:139
-        pix = tv.clone()                                                           # visibility.py:38-40 pixel mapping
-        pix[..., 0] = tv[..., 0] * W / 2 + W / 2
-        pix[..., 1] = tv[..., 1] * H / 2 + H / 2
-        pix[..., 2] = tv[..., 2] - tv[..., 2].min() + 1
+        pix = tv.clone()
+        if self.convention == "pytorch3d":
+            pix[..., :2] = -pix[..., :2]                                           # renderer.py:54-55, NDC in
+            depth0 = float("inf")
+        else:                                                                      # visibility.py:38-40 pixel mapping
+            pix[..., 0] = tv[..., 0] * W / 2 + W / 2
+            pix[..., 1] = tv[..., 1] * H / 2 + H / 2
+            pix[..., 2] = tv[..., 2] - tv[..., 2].min() + 1
+            depth0 = 1e6
         fv = face_vertices(pix, self.faces).contiguous()
         normals = vertex_normals(vertices.float(), self.faces)                     # renderer.py:143
         fn = face_vertices(normals, self.faces).contiguous()
-        depth = torch.full((B, H, W), 1e6, device=fv.device)
+        depth = torch.full((B, H, W), depth0, device=fv.device)
         tri = torch.full((B, H, W), -1, dtype=torch.int32, device=fv.device)
         bary = torch.zeros((B, H, W, 3), device=fv.device)
-        rasterize.standard_rasterize(fv, depth, tri, bary, H, W)
+        rasterize._forward(fv, None, depth, tri, bary, H, W, convention=self.convention)
         tex = torch.empty((B, H, W, 3), device=fv.device)
         nrm = torch.empty((B, H, W, 3), device=fv.device)
         cond = torch.empty((B, H, W, 6), device=fv.device) if want_cond else None

@@ -180,13 +180,32 @@ size_t gifb200_rasterize_workspace_bytes(int B, int F, int h, int w);
 int gifb200_rasterize_fwd(const float* face_vertices, const float* face_colors, float* depth, int32_t* triangle,
                           float* out3, int B, int F, int h, int w, void* workspace, size_t workspace_bytes,
                           gifb200_stream_t stream);
-/* Backward (absent in the reference): given the forward's triangle buffer and upstream gradients of the
- * barycentric weights g_bary (B,h,w,3) and/or interpolated colours g_img (B,h,w,3) and/or depth g_depth (B,h,w)
- * (each may be NULL), accumulates into g_face_vertices (B,F,3,3) and g_face_colors (B,F,3,3) (may be NULL).
- * Both gradient outputs must be zero-initialised by the caller (scatter-add). */
+/* Extended form.  convention 0 = the in-repo standard_rasterize semantics above.  convention 1 = pytorch3d's
+ * rasterize_meshes as Pytorch3dRasterizer.forward calls it (my_utils/photometric_optimization/renderer.py:35-67:
+ * image_size, blur_radius 0, faces_per_pixel 1, perspective_correct False) -- the rasteriser the reference's conditioning
+ * maps are made with: face_vertices in NDC with x, y already negated by the caller (renderer.py:55), +X left / +Y up,
+ * pixel (yi,xi) samples NDC (-1 + (2(W-1-xi)+1)/W, -1 + (2(H-1-yi)+1)/H), edge-function barycentrics over (area + 1e-8),
+ * no back-face culling, strictly-inside test, linear depth sum w_i z_i >= 0; depth/triangle/out3 = zbuf / face index within
+ * the mesh / barycentrics, still updated in place (initialise depth to +inf; the binding maps empty pixels to the -1 that
+ * pytorch3d returns).  The fork the reference pins is absent (requirements.txt:36): parity unpinned, checked against the
+ * restatement in oracle/rasterize_oracle.c.
+ * face_colors2 / out3b (both may be NULL): a second per-corner attribute set interpolated in the same pass, e.g. vertex
+ * colours and vertex normals of BASELINE.json configs[3] ("texture+normal render") from ONE rasterisation. */
+int gifb200_rasterize_fwd_ex(const float* face_vertices, const float* face_colors, const float* face_colors2, float* depth,
+                             int32_t* triangle, float* out3, float* out3b, int B, int F, int h, int w, int convention,
+                             void* workspace, size_t workspace_bytes, gifb200_stream_t stream);
+/* Backward (absent in the reference for standard_rasterize; provided by pytorch3d for convention 1): given the
+ * forward's triangle buffer and upstream gradients of the barycentric weights g_bary (B,h,w,3) and/or interpolated
+ * colours g_img (B,h,w,3) and/or depth g_depth (B,h,w) (each may be NULL), writes g_face_vertices (B,F,3,3) and
+ * g_face_colors (B,F,3,3) (may be NULL).  Outputs are OVERWRITTEN (one thread per face gathers the pixels it owns: no
+ * atomics, no zero-initialisation needed, deterministic). */
 int gifb200_rasterize_bwd(const float* face_vertices, const float* face_colors, const int32_t* triangle,
                           const float* g_bary, const float* g_img, const float* g_depth, float* g_face_vertices,
                           float* g_face_colors, int B, int F, int h, int w, gifb200_stream_t stream);
+int gifb200_rasterize_bwd_ex(const float* face_vertices, const float* face_colors, const float* face_colors2,
+                             const int32_t* triangle, const float* g_bary, const float* g_img, const float* g_img2,
+                             const float* g_depth, float* g_face_vertices, float* g_face_colors, float* g_face_colors2,
+                             int B, int F, int h, int w, int convention, gifb200_stream_t stream);
 
 /* Fused shading epilogue of the FLAME conditioning render: from the rasteriser's (triangle, bary) buffers to the textured
  * image tex (B,h,w,3) = albedo(uv) * SH-shading(normal) * alpha, the normal image nrm (B,h,w,3), and the quantised

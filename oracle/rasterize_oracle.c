@@ -97,3 +97,63 @@ void oracle_standard_rasterize_colors(const float* face_vertices, const float* f
                                       int32_t* tri, float* images, int batch, int ntri, int h, int w) {
     rasterize(face_vertices, face_colors, depth, tri, images, batch, ntri, h, w);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * pytorch3d `rasterize_meshes` as the reference calls it -- the rasteriser its conditioning maps are made with
+ * (my_utils/photometric_optimization/renderer.py:35-67: image_size S, blur_radius 0, faces_per_pixel 1, bin_size None,
+ * perspective_correct False; the caller negates x and y first, renderer.py:55).
+ *
+ * PARITY UNPINNED: pytorch3d is a third-party dependency, the reference pins an unversioned fork
+ * (requirements.txt:36: git+https://github.com/ParthaEth/pytorch3d.git, no commit/tag; submodule README: PyTorch3D 0.2) that
+ * is absent from /root/reference, and the reference holds no test or golden output at this boundary.  What
+ * follows restates the PUBLISHED algorithm of pytorch3d 0.2's naive rasteriser (csrc/rasterize_meshes/rasterize_meshes.cu:
+ * RasterizeMeshesNaiveCudaKernel / CheckPixelInsideFace; csrc/rasterize_meshes/geometry_utils.cuh: EdgeFunctionForward,
+ * BarycentricCoordsForward, CheckPointOutsideBoundingBox; rasterization_utils.cuh: PixToNdc); the coarse-to-fine path the
+ * heuristic bin_size selects gives the same result as long as no bin overflows.  Rules:
+ *   - NDC axes +X left, +Y up: output pixel (yi, xi) samples p = (PixToNdc(W-1-xi, W), PixToNdc(H-1-yi, H)),
+ *     PixToNdc(i, S) = -1 + (2 i + 1) / S;
+ *   - a face is skipped if max z < 0, if |EdgeFunction(v0,v1,v2)| <= kEpsilon (1e-8), or if p lies outside its xy bbox;
+ *   - barycentrics w0 = E(p,v1,v2)/A, w1 = E(p,v2,v0)/A, w2 = E(p,v0,v1)/A with A = E(v2,v0,v1) + kEpsilon,
+ *     E(p,a,b) = (p.x-a.x)(b.y-a.y) - (p.y-a.y)(b.x-a.x); no back-face culling;
+ *   - pz = w0 z0 + w1 z1 + w2 z2 (perspective_correct False); skipped if pz < 0;
+ *   - blur_radius 0: kept only if w0, w1, w2 > 0 (strictly inside);
+ *   - faces_per_pixel 1: the smallest pz wins; on an exact tie the earlier (lower-index) face stays.
+ * Outputs (in place, like the rest of this file): depth = zbuf (caller initialises it, e.g. +inf), tri = face index within
+ * the mesh (pytorch3d's pix_to_face adds the packed offset b*F), out3 = barycentrics.  fp32, no FMA contraction.
+ * (kEpsilon: 1e-8 as in pytorch3d's float_math.cuh of the 0.2 line; unpinned like the rest.) */
+static float p3d_pix_to_ndc(int i, int S) { return -1.0f + (2 * i + 1.0f) / S; }
+
+static float p3d_edge(float px, float py, float ax, float ay, float bx, float by) {
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+}
+
+void oracle_rasterize_pytorch3d(const float* fv, float* depth, int32_t* tri, float* bary, int batch, int ntri, int h, int w) {
+    const float eps = 1e-8f;
+    for (int b = 0; b < batch; ++b)
+        for (int yi = 0; yi < h; ++yi)
+            for (int xi = 0; xi < w; ++xi) {
+                const float xf = p3d_pix_to_ndc(w - 1 - xi, w), yf = p3d_pix_to_ndc(h - 1 - yi, h);
+                size_t pix = ((size_t)b * h + yi) * w + xi;
+                int owner = INT32_MAX;
+                for (int f = 0; f < ntri; ++f) {
+                    const float* fc = fv + ((size_t)b * ntri + f) * 9;
+                    float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
+                    if (fmaxf(z0, fmaxf(z1, z2)) < 0.0f) continue;
+                    float area = p3d_edge(x0, y0, x1, y1, x2, y2);
+                    if (area <= eps && area >= -eps) continue;
+                    if (xf > fmaxf(x0, fmaxf(x1, x2)) || xf < fminf(x0, fminf(x1, x2)) ||
+                        yf > fmaxf(y0, fmaxf(y1, y2)) || yf < fminf(y0, fminf(y1, y2))) continue;
+                    float A = p3d_edge(x2, y2, x0, y0, x1, y1) + eps;
+                    float w0 = p3d_edge(xf, yf, x1, y1, x2, y2) / A;
+                    float w1 = p3d_edge(xf, yf, x2, y2, x0, y0) / A;
+                    float w2 = p3d_edge(xf, yf, x0, y0, x1, y1) / A;
+                    float pz = w0 * z0 + w1 * z1 + w2 * z2;
+                    if (pz < 0.0f) continue;
+                    if (!(w0 > 0.0f && w1 > 0.0f && w2 > 0.0f)) continue;
+                    int take = (pz < depth[pix]) || (pz == depth[pix] && f < owner);
+                    if (!take) continue;
+                    depth[pix] = pz; owner = f; tri[pix] = f;
+                    bary[pix * 3 + 0] = w0; bary[pix * 3 + 1] = w1; bary[pix * 3 + 2] = w2;
+                }
+            }
+}

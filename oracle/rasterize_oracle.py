@@ -22,7 +22,9 @@ _ip = ctypes.POINTER(ctypes.c_int32)
 
 
 def _lib(path, build_target):
-    if not os.path.isfile(path):
+    src = os.path.join(_HERE, "rasterize_oracle.c")
+    stale = build_target == "oracle" and os.path.isfile(path) and os.path.getmtime(path) < os.path.getmtime(src)
+    if not os.path.isfile(path) or stale:
         import subprocess
         subprocess.run(["make", "-C", _HERE, build_target], check=True, capture_output=True)
     return ctypes.CDLL(path)
@@ -62,6 +64,24 @@ def oracle_rasterize(fv, h, w, depth=None, tri=None, bary=None):
 
 def oracle_rasterize_colors(fv, colors, h, w, depth=None, tri=None, images=None):
     return _run(_lib(_ORACLE_SO, "oracle"), "oracle", fv, colors, h, w, depth, tri, images)
+
+
+def oracle_rasterize_pytorch3d(fv_ndc, h, w):
+    """pytorch3d ``rasterize_meshes`` conventions (oracle/rasterize_oracle.c, PARITY UNPINNED): face vertices in NDC (x, y
+    already negated like renderer.py:55) -> (zbuf (B,h,w) with -1 where empty, pix_to_face (B,h,w) index within the mesh
+    or -1, bary (B,h,w,3) with -1 where empty) -- the values pytorch3d returns for faces_per_pixel = 1."""
+    lib = _lib(_ORACLE_SO, "oracle")
+    fv = np.ascontiguousarray(fv_ndc, np.float32)
+    batch, ntri = fv.shape[:2]
+    depth = np.full((batch, h, w), np.inf, np.float32)
+    tri = np.full((batch, h, w), -1, np.int32)
+    bary = np.full((batch, h, w, 3), -1.0, np.float32)
+    lib.oracle_rasterize_pytorch3d.restype = None
+    lib.oracle_rasterize_pytorch3d(fv.ctypes.data_as(_fp), depth.ctypes.data_as(_fp), tri.ctypes.data_as(_ip),
+                                   bary.ctypes.data_as(_fp), ctypes.c_int(batch), ctypes.c_int(ntri), ctypes.c_int(h),
+                                   ctypes.c_int(w))
+    depth[tri < 0] = -1.0
+    return depth, tri, bary
 
 
 def ref_rasterize(fv, h, w, depth=None, tri=None, bary=None):

@@ -10,14 +10,17 @@ from oracle import render_oracle as RD
 pytestmark = pytest.mark.gpu
 
 
-def test_render_matches_oracle(cuda):
+@pytest.mark.parametrize("convention", ["pytorch3d", "standard"])
+def test_render_matches_oracle(cuda, convention):
+    """Both rasterisation conventions: "pytorch3d" is what the reference's Renderer really uses (renderer.py:46-84, parity
+    unpinned), "standard" the in-repo kernels' semantics."""
     from gif_b200.flame_synth import flame_topology, flame_uv, synthetic_flame_params
     from gif_b200.render import FlameRenderer, batch_orth_proj, vertex_normals
     B, S = 3, 256
     verts, cam, alb, lights = synthetic_flame_params(B, seed=1)
     _, faces = flame_topology()
     uv, uvf = flame_uv()
-    R = FlameRenderer(faces, uv, uvf, image_size=S).to(cuda)
+    R = FlameRenderer(faces, uv, uvf, image_size=S, convention=convention).to(cuda)
     tex, nrm, cond = R.render_tex_and_normal(verts.to(cuda), cam.to(cuda), alb.to(cuda), lights.to(cuda))
     # ---- oracle
     trans = RD.batch_orth_proj(verts, cam)
@@ -25,10 +28,15 @@ def test_render_matches_oracle(cuda):
     tv = trans.clone()
     tv[:, :, 2] += 10
     pix = tv.clone()
-    pix[..., 0] = tv[..., 0] * S / 2 + S / 2
-    pix[..., 1] = tv[..., 1] * S / 2 + S / 2
-    pix[..., 2] = tv[..., 2] - tv[..., 2].min() + 1
-    d, t, b = RO.oracle_rasterize(pix[:, faces].numpy(), S, S)
+    if convention == "pytorch3d":
+        pix[..., :2] = -pix[..., :2]                                   # renderer.py:55
+        d, t, b = RO.oracle_rasterize_pytorch3d(pix[:, faces].numpy(), S, S)
+        b = b * (t >= 0)[..., None]                                    # the shade kernel / renderer.py:81 zero the empties
+    else:
+        pix[..., 0] = tv[..., 0] * S / 2 + S / 2
+        pix[..., 1] = tv[..., 1] * S / 2 + S / 2
+        pix[..., 2] = tv[..., 2] - tv[..., 2].min() + 1
+        d, t, b = RO.oracle_rasterize(pix[:, faces].numpy(), S, S)
     uvg = torch.cat([uv, torch.ones_like(uv[:, :1])], -1) * 2 - 1
     uvg[:, 1] = -uvg[:, 1]
     n = RD.vertex_normals(verts, faces)
