@@ -15,13 +15,21 @@ weights are random-initialised as the reference's constructors do.
   value        images/sec, whole job, inputs resident in HBM, CUDA-event timed, max over ranks.
   e2e          same loop, but every step copies that step's inputs from PINNED HOST memory and reads the two loss
                scalars back (the call a user of train.py makes: host batch in, losses out).
+  precision    --precision bf16x3 (default, the headline): the error-compensated tensor-core contraction, the mode that
+               holds BASELINE.json's 1e-3 bar end to end (tests/test_models_gpu.py); the same step in plain kind::tf32
+               (faster, ~1e-3 forward / 1e-2 R1 deviation) is measured too and reported under "tf32_mode".
   roofline     the dominant kernel = the tcgen05 implicit-GEMM convolution (conv_tc_kernel): algorithmic FLOPs of
-               every launch inside the timed region / its CUDA-event duration, against the tf32 tensor peak
-               (= half of MEASURED_PEAKS.json's sustained bf16 figure -- the file has no tf32 entry).
-  cpu_baseline the oracle port of the reference (oracle/stylegan2_oracle.py, torch CPU, all host threads) on a
-               bounded sample: ONE iteration at batch 1 without R1/PPL (~10-30 s).
-  --impl reference   times only that CPU arm (the reference is Python and cannot travel to the GPU box; the port is
-               pinned to it at 1e-15 in fp64, tests/golden/ORACLE_VS_REFERENCE.txt).
+               every launch / its CUDA-event duration.  Peak: bf16x3 issues three kind::f16 MMAs per algorithmic MAC, so
+               its ceiling is MEASURED_PEAKS.json's sustained bf16 figure / 3; tf32: the cuBLAS TF32 GEMM rate measured
+               on this pool with the same protocol (profiles/r02_tf32_peak.json, tools/measure_tf32_peak.py).
+  cpu_baseline the REFERENCE ITSELF on the host cores: its unmodified train() (train.py:80-252) over its own model / loss
+               modules (build-time extract oracle/_ref/pyref, oracle/ref_import.py), fp32, all usable threads, on a bounded
+               sample: batch 1, one R1 iteration and one plain iteration combined with the loop's 1/16 R1 share (~1 min;
+               the reference's CPU formulation needs ~25-50 s per image and iteration).  Falls back to the oracle port
+               (kind "port") if the extract is absent.
+  --impl reference   times only that CPU arm (plus a warm-up iteration), rank 0 only.
+  extras       BASELINE.json configs[1] (generator forward 256^2 bs16) and configs[3] (FLAME-topology texture+normal
+               rasterisation 256^2 bs64, forward and forward+backward, with its HBM roofline fraction).
 """
 import argparse
 import json
@@ -69,8 +77,11 @@ def parse():
     ap.add_argument("--texture-loss", action="store_true",
                     help="also time the step of the flagship reference run: no PPL, + texture-space interpolation loss")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying CUDA graphs")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "bf16x3"],
-                    help="contraction mode of the tensor-core kernels (gif_b200.ops.set_precision)")
+    ap.add_argument("--precision", default="bf16x3", choices=["tf32", "bf16x3"],
+                    help="contraction mode of the tensor-core kernels for the HEADLINE numbers (gif_b200.ops.set_precision); "
+                         "the other mode is measured as an extra")
+    ap.add_argument("--no-other-precision", action="store_true", help="skip the extra measurement in the other precision mode")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] / configs[3] side measurements")
     return ap.parse_args()
 
 
@@ -173,22 +184,127 @@ def cpu_arm(steps, warmup, budget_s=None):
                       f"(torch CPU fp32, {cores} threads), {dt:.1f} s per iteration"}
 
 
+def cpu_arm_reference(batch, warm_up, vocab=1000):
+    """The reference's own loop and modules on the host cores (kind "reference"): iterations of the UNMODIFIED train() with the
+    loop counter at [14 (warm-up, optional),] 15 (carries the R1 penalty, train.py:145) and 16 (plain).  Measured in the
+    build container (8 cores): 49 s per plain iteration and 99 s per R1 iteration PER IMAGE -- the reference's grouped
+    per-sample-weight convolutions and its conv2d-based upfirdn2d are ~25x slower on a CPU than the oracle port's
+    modulate-input form -- hence batch 1 and two or three iterations: a bounded sample."""
+    from oracle import ref_import, ref_train_runner
+    if not ref_import.available():
+        return None
+    cores = usable_cores()
+    torch.set_num_threads(cores)
+    ref = ref_import.load()
+    train = ref_import.load_train(with_gif_b200=False)
+    kw = dict(embedding_vocab_size=vocab, rendered_flame_ascondition=True, normal_maps_as_cond=True, core_tensor_res=4, n_mlp=8)
+    import contextlib
+    with contextlib.redirect_stdout(None):
+        G, Gr = ref.gen.StyledGenerator(**kw), ref.gen.StyledGenerator(**kw)
+        D = ref.disc.Discriminator(size=RES, num_color_chnls=9, channel_multiplier=2)
+    gen = torch.Generator().manual_seed(99)
+    n = 3 if warm_up else 2
+    batches = [(torch.rand(batch, 3, RES, RES, generator=gen) * 2 - 1, torch.rand(batch, 6, RES, RES, generator=gen) * 2 - 1,
+                torch.randn(batch, 159, generator=gen), torch.randint(0, vocab, (batch,), generator=gen)) for _ in range(n)]
+    stamps = []
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_train_runner.run(train, G, D, Gr, batches, RES, vocab, first_i=14 if warm_up else 15, force_cpu=True, stamps=stamps)
+    durs = [stamps[k + 1] - stamps[k] for k in range(n)]
+    r1, plain = durs[-2], durs[-1]
+    per_iter = (15 * plain + r1) / 16                       # the loop's R1 share (every 16th iteration)
+    return {"value": batch / per_iter, "unit": "images/sec", "cores": cores, "kind": "reference", "steps_done": n,
+            "s_per_iteration": {"plain": plain, "with_r1": r1, **({"warm_up": durs[0]} if warm_up else {})},
+            "sample": f"the reference's unmodified train() (train.py:80-252) over its own model/ and loss modules, fp32 torch "
+                      f"CPU, {cores} threads, batch {batch} at 256x256: {n} iterations ("
+                      + (f"warm-up {durs[0]:.1f} s, " if warm_up else "") +
+                      f"R1 iteration {r1:.1f} s, plain {plain:.1f} s) combined as (15 plain + 1 R1) / 16; no path-length term "
+                      f"(the reference's own is unrunnable, SURVEY 8 L2)"}
+
+
+def cpu_baseline(batch, warm_up, port_budget_s):
+    """The reference itself when its files are here (build-time extract / the container's tree), else the oracle port."""
+    try:
+        cb = cpu_arm_reference(batch, warm_up)
+    except Exception as e:      # the baseline must never take the bench line down with it
+        sys.stderr.write(f"reference CPU arm failed ({type(e).__name__}: {e}); falling back to the oracle port\n")
+        cb = None
+    return cb if cb is not None else cpu_arm(3, 1, budget_s=port_budget_s)
+
+
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # K steps / W warm-ups as asked, each step a bounded sample (one batch-1 iteration), the whole run capped at ~3 minutes
-    cb = cpu_arm(max(1, args.steps), max(0, args.warmup), budget_s=180.0)
+    # the reference arm: batch 1, three iterations (warm-up, R1, plain) of the reference's own train(): ~2-3 minutes of CPU work
+    cb = cpu_baseline(1, True, port_budget_s=180.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
             "steps": cb["steps_done"], "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "train_step_256_bs32 (CPU arm: bounded sample at batch 1, see cpu_baseline.sample)"},
+            "config": {"workload": "train_step_256_bs32: StyledGenerator + Discriminator(256, 9ch), D step + G step, Adam, EMA, R1 "
+                                   "every 16th iteration (CPU arm: bounded sample at batch 1, see cpu_baseline.sample)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def side_measurements(dev, trainer, resident):
+    """BASELINE.json configs[1] and configs[3], measured in the driver-run bench so that they appear in the bench line."""
+    from gif_b200 import rasterize
+    from gif_b200.flame_synth import synthetic_flame_batch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    out = {}
+    # configs[1]: StyledGenerator forward 256^2 bs16 (105.3 GFLOP / image, SURVEY 8d)
+    G = trainer.g_running
+    cond, idx = resident[0][1][:16], resident[0][2][:16]
+    with torch.no_grad():
+        ms = timeit(lambda: G(cond, step=6, input_indices=idx))
+    out["config1_generator_fwd_256_bs16"] = {"images_per_s": 16 / ms * 1e3, "ms": ms, "tflops_algorithmic": 16 * 105.3 / ms}
+    # configs[3]: FLAME-topology texture + normal rasterisation 256^2 bs64 (one pass, two attribute sets), fwd and fwd+bwd
+    b, h, w = 64, 256, 256
+    fv, fc = synthetic_flame_batch(b, h, w, seed=0, device=dev)
+    F = fv.shape[1]
+    nrm = torch.rand_like(fc)
+    fvg, fcg, ng = fv.clone().requires_grad_(True), fc.clone().requires_grad_(True), nrm.clone().requires_grad_(True)
+    g1 = torch.randn(b, h, w, 3, device=dev)
+
+    def fwd_bwd():
+        _, _, im, nm = rasterize.rasterize(fvg, h, w, fcg, ng)
+        torch.autograd.backward([im, nm], [g1, g1])
+    ms_f = timeit(lambda: rasterize.rasterize(fv, h, w, fc, nrm))
+    ms_fb = timeit(fwd_bwd)
+    fwd_bytes = 3 * F * 36 + h * w * (4 + 4 + 12 + 12)                  # SURVEY 8d, texture+normal: 3.96 MB / image
+    bwd_bytes = h * w * (12 + 12 + 4) + 3 * F * 36 + 3 * F * 36
+    hbm = 6487.4
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except (OSError, KeyError):
+        pass
+    out["config3_rasterize_texture_normal_256_bs64"] = {
+        "renders_per_s_fwd": b / ms_f * 1e3, "renders_per_s_fwd_bwd": b / ms_fb * 1e3, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
+        "roofline": {"bound": "hbm", "achieved": b * fwd_bytes / ms_f / 1e6, "peak": hbm, "unit": "GB/s",
+                     "frac": b * fwd_bytes / ms_f / 1e6 / hbm, "frac_fwd_bwd": b * (fwd_bytes + bwd_bytes) / ms_fb / 1e6 / hbm,
+                     "algorithmic_bytes_per_image": {"fwd": fwd_bytes, "bwd": bwd_bytes}}}
+    return out
+
+
 def main():
     args = parse()
     # Libraries (NCCL prints its version banner) write to stdout: keep fd 1 for the ONE JSON line, send the rest to stderr.
@@ -201,6 +317,7 @@ def main():
     from gif_b200 import _lib, ops
     from gif_b200.distributed import broadcast_module, init_from_env
     from gif_b200.train_step import GifTrainer
+    from gif_b200 import losses as losses_mod
     import torch.distributed as dist
 
     rank, world, local = init_from_env("nccl")
@@ -353,6 +470,48 @@ def main():
         except Exception as e:
             extra_tex = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         trainer.interp_tex_loss = None
+    other_mode = None
+    if not args.no_other_precision:
+        # the same step (same flags as the headline line: with the path-length term unless --no-ppl) in the other mode
+        other = "tf32" if args.precision == "bf16x3" else "bf16x3"
+        ops.set_precision(other)
+        saved_ppl = trainer.ppl
+        trainer.ppl = None if args.no_ppl else losses_mod.PathLengthRegularizor()
+        trainer._graphs = None
+        try:
+            trainer.iteration = 13
+            run(3, False)
+            if not args.no_graph:
+                trainer.capture(B, RES)
+                trainer.iteration = 14
+                run(2, False)
+            ms_o = timed(args.steps, False)
+            other_mode = {"precision": other, "value": world * B * args.steps / (ms_o / 1000.0), "unit": "images/sec",
+                          "ms_per_step": ms_o / args.steps}
+            if trainer.ppl is not None:
+                trainer.ppl = None
+                trainer._graphs = None
+                if not args.no_graph:
+                    trainer.capture(B, RES)
+                    trainer.iteration = 14
+                    run(2, False)
+                else:
+                    trainer.iteration = 13
+                    run(3, False)
+                ms_o2 = timed(args.steps, False)
+                other_mode["same_step_without_path_length_reg"] = {"value": world * B * args.steps / (ms_o2 / 1000.0),
+                                                                   "ms_per_step": ms_o2 / args.steps}
+        except Exception as e:
+            other_mode = {"precision": other, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+        trainer.ppl = saved_ppl
+        trainer._graphs = None
+        ops.set_precision(args.precision)
+    extras = None
+    if rank == 0 and not args.no_extras:
+        try:
+            extras = side_measurements(dev, trainer, resident)
+        except Exception as e:
+            extras = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -373,13 +532,27 @@ def main():
         tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
         tot_fl = sum(f for _, _, f, _ in prof)
         prof_steps = min(args.steps, 4) if use_graph else args.steps
-        peaks = {}
+        peaks, tf32pk = {}, {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        try:
+            tf32pk = json.load(open(os.path.join(ROOT, "profiles", "r02_tf32_peak.json")))
+        except OSError:
+            pass
         bf16 = peaks.get("bf16_tflops_sustained")
-        peak = bf16 / 2 if bf16 else 1400.0 / 2
+        if args.precision == "bf16x3":
+            # three kind::f16 (bf16) MMAs per algorithmic multiply-add: the ceiling for ALGORITHMIC flops is bf16 peak / 3
+            peak = (bf16 if bf16 else 1400.0) / 3
+            peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained / 3 (bf16x3 issues hi*hi + hi*lo + lo*hi: three bf16 MMAs per "
+                        "algorithmic multiply-add)") if bf16 else "fallback 1.4 PFLOP/s sustained bf16 / 3"
+        else:
+            t32 = tf32pk.get("tf32_tflops_sustained")
+            peak = t32 if t32 else (bf16 / 2 if bf16 else 700.0)
+            peak_src = ("profiles/r02_tf32_peak.json tf32_tflops_sustained (cuBLAS fp32 GEMM with TF32 tensor cores, 8192^3, 4 s "
+                        "back to back, measured on this pool with MEASURED_PEAKS.json's protocol)") if t32 else \
+                       "MEASURED_PEAKS.json bf16_tflops_sustained / 2"
         ach_all = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
         ns = [(a.elapsed_time(b), f) for a, b, f, tag in prof if tag == "northstar"]
         # dominant kernel instance: conv_tc_kernel<128> on the north-star layer (B,128,256,256)->128, 3x3:
@@ -387,32 +560,39 @@ def main():
         ach = (sum(f for _, f in ns) / (sum(t for t, _ in ns) * 1e-3) / 1e12) if ns else ach_all
         traffic = None
         try:    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["conv_tc_northstar_dram_bytes_per_launch"]
-        except (OSError, KeyError, ValueError):
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            traffic = tj["conv_tc_northstar_dram_bytes_per_launch"][args.precision]
+        except (OSError, KeyError, ValueError, TypeError):
             pass
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<128> (tcgen05 kind::tf32 implicit GEMM) on the north-star layer "
-                                             "ModulatedConv2d 128->128 3x3 @256x256, batch 32",
+        kname = ("conv_tc_kernel<128, X3> (tcgen05 kind::f16, bf16x3 error-compensated implicit GEMM)" if args.precision == "bf16x3"
+                 else "conv_tc_kernel<128> (tcgen05 kind::tf32 implicit GEMM)")
+        roof = {"bound": "tensor", "kernel": kname + " on the north-star layer ModulatedConv2d 128->128 3x3 @256x256, batch 32",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_flops_per_launch": 2.0 * 9 * 128 * 128 * 32 * 256 * 256,
                 "algorithmic_hbm_bytes_per_launch": 2 * 32 * 256 * 256 * 128 * 4 + 9 * 128 * 128 * 4,
                 "launches_of_this_shape": len(ns), "avg_launch_ms": (sum(t for t, _ in ns) / len(ns)) if ns else None,
                 "all_tensor_core_conv_launches": {"achieved": ach_all, "frac": ach_all / peak},
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 runs at half the bf16 rate; no tf32 entry"
-                                " in the file)") if bf16 else "fallback 1.4 PFLOP/s sustained bf16 / 2",
+                "peak_source": peak_src,
+                "executed_mma_tflops": ach * (3 if args.precision == "bf16x3" else 1),
                 "launches": len(prof), "kernel_ms_per_step": tot_ms / prof_steps,
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note}
     cb = None
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N=1 measurement
-        cb = cpu_arm(3, 1, budget_s=40.0)             # ~10-30 s of CPU work on the box's host cores
+        cb = cpu_baseline(1, False, port_budget_s=40.0)   # the reference's own train() at batch 1: an R1 and a plain iteration
     line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 tensor-core contraction, f32 accumulate/storage", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": ("bf16x3 error-compensated tensor-core contraction (two-term bf16 operands, 3 MMAs per slice), f32 accumulate/storage"
+                      if args.precision == "bf16x3" else "tf32 tensor-core contraction, f32 accumulate/storage"),
+            "precision": args.precision, "data": "synthetic",
             "config": {"workload": "train_step_256_bs32: StyledGenerator(70000 ids) + Discriminator(256, 9ch), D step + G step, "
                                    "Adam, EMA, R1 every 16th iteration" + ("" if args.no_ppl else ", path-length reg every iteration"),
                        "global_batch": B * world, "resolution": RES, "parallelism": f"dp{world}", "cuda_graph": graph_note,
                        "l2_policy": "inputs (4 x 75.5 MB batches, 1+ GB activations per layer) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb,
             "same_step_without_path_length_reg": extra_no_ppl,
+            ("tf32_mode" if args.precision == "bf16x3" else "bf16x3_mode"): other_mode,
+            "other_configs": extras,
             "same_step_with_texture_interpolation_loss_instead_of_ppl": extra_tex}
     emit(line)
     if world > 1:

@@ -214,6 +214,21 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(const float* __restrict_
 // 16-byte-per-lane variants of the two kernels above for C % 32 == 0 (every layer of the model): a thread owns 4
 // channels, TX lanes span TX*4 channels of one pixel row, 256/TX rows per block step; the row loop is unrolled so
 // that 8-12 independent 16-byte loads are in flight per thread (the scalar kernels reach ~2.7 TB/s, these ~HBM rate).
+// four consecutive elements of the two-term bf16 expansion (hi plane at planes[e], lo plane at planes[total + e])
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ planes, long long total, long long e, const float4& t) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(t.x), h1 = __float2bfloat16_rn(t.y), h2 = __float2bfloat16_rn(t.z),
+                        h3 = __float2bfloat16_rn(t.w);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(t.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(t.y - __bfloat162float(h1)),
+                        l2 = __float2bfloat16_rn(t.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(t.w - __bfloat162float(h3));
+    uint2 ph, pl;
+    ph.x = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    ph.y = static_cast<uint32_t>(__bfloat16_as_ushort(h2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h3)) << 16);
+    pl.x = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    pl.y = static_cast<uint32_t>(__bfloat16_as_ushort(l2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l3)) << 16);
+    *reinterpret_cast<uint2*>(planes + e) = ph;
+    *reinterpret_cast<uint2*>(planes + total + e) = pl;
+}
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 __device__ __forceinline__ float4 f4_round(float4 v) {
@@ -228,7 +243,9 @@ __global__ void __launch_bounds__(256) tail_bwd_vec_kernel(const float* __restri
                                                            const float* __restrict__ acc, const float* __restrict__ d,
                                                            float* __restrict__ gt, float* __restrict__ gacc,
                                                            float* __restrict__ gb, float* __restrict__ gd, int rows, int C,
-                                                           int rows_per_block, float slope, float gain, int rtf32) {
+                                                           int rows_per_block, float slope, float gain, int rtf32,
+                                                           __nv_bfloat16* __restrict__ gt_planes,
+                                                           __nv_bfloat16* __restrict__ gacc_planes, long long total) {
     constexpr int TY = 256 / TX;
     __shared__ float4 sm[2][TY][TX];
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
@@ -254,8 +271,10 @@ __global__ void __launch_bounds__(256) tail_bwd_vec_kernel(const float* __restri
         }
         float4 ga = make_float4(g.x * dv.x, g.y * dv.y, g.z * dv.z, g.w * dv.w);
         if (rtf32) { g = f4_round(g); ga = f4_round(ga); }
-        *reinterpret_cast<float4*>(gt + i) = g;
+        if (gt) *reinterpret_cast<float4*>(gt + i) = g;
         if (gacc) *reinterpret_cast<float4*>(gacc + i) = ga;
+        if (gt_planes) store_planes4(gt_planes, total, i, g);          // bf16x3 operands of the consuming dgrad / wgrad
+        if (gacc_planes) store_planes4(gacc_planes, total, i, ga);
     }
     sm[0][ty][tx] = sb;
     sm[1][ty][tx] = sd;
@@ -732,9 +751,11 @@ int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int 
     return GIFB200_OK;
 }
 
-int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
-                     float* gb, float* gd, int B, int P, int C, float slope, float gain, int rtf32, gifb200_stream_t stream) {
+static int tail_bwd_impl(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
+                         float* gb, float* gd, int B, int P, int C, float slope, float gain, int rtf32, void* gt_planes,
+                         void* gacc_planes, gifb200_stream_t stream) {
     GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "tail_bwd: bad shape");
+    GIFB200_REQUIRE(gt || gt_planes, GIFB200_E_SHAPE, "tail_bwd: gt or gt_planes is required");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B == 0) return GIFB200_OK;
     if (gb) {
@@ -746,20 +767,25 @@ int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const fl
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "tail_bwd memset", cudaGetErrorString(e));
     }
     if (P == 0) return GIFB200_OK;
-    if (C % 32 == 0 && aligned16(gy) && aligned16(y) && aligned16(gt) && (!gd || aligned16(acc)) && (!gacc || aligned16(gacc)) &&
-        (!d || aligned16(d))) {
+    const bool planes = gt_planes || gacc_planes;
+    if (C % 32 == 0 && aligned16(gy) && aligned16(y) && (!gt || aligned16(gt)) && (!gd || aligned16(acc)) && (!gacc || aligned16(gacc)) &&
+        (!d || aligned16(d)) && (!gt_planes || aligned16(gt_planes)) && (!gacc_planes || aligned16(gacc_planes))) {
         const int tx = vec_lanes(C);
         int rpb;
         const int cbv = C / (4 * tx);
         const int rb = rows_split_vec(P, cbv, B, 256 / tx, &rpb);
         GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "tail_bwd: grid too large");
         const dim3 grid(cbv, rb, B);
-        if (tx == 32) tail_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
-        else if (tx == 16) tail_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
-        else tail_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
+        __nv_bfloat16* p1 = static_cast<__nv_bfloat16*>(gt_planes);
+        __nv_bfloat16* p2 = static_cast<__nv_bfloat16*>(gacc_planes);
+        const long long total = static_cast<long long>(B) * P * C;
+        if (tx == 32) tail_bwd_vec_kernel<32><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32, p1, p2, total);
+        else if (tx == 16) tail_bwd_vec_kernel<16><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32, p1, p2, total);
+        else tail_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32, p1, p2, total);
         GIFB200_LAUNCH_CHECK("tail_bwd_vec_kernel");
         return GIFB200_OK;
     }
+    GIFB200_REQUIRE(!planes && gt, GIFB200_E_ALIGN, "tail_bwd: the planes outputs need C % 32 == 0 and 16-byte aligned pointers");
     const int cb = cdiv(C, 32);
     int rpb;
     const int rb = rows_split(P, cb, B, &rpb);
@@ -767,6 +793,17 @@ int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const fl
     tail_bwd_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gy, y, acc, d, gt, gacc, gb, gd, P, C, rpb, slope, gain, rtf32);
     GIFB200_LAUNCH_CHECK("tail_bwd_kernel");
     return GIFB200_OK;
+}
+
+int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
+                     float* gb, float* gd, int B, int P, int C, float slope, float gain, int rtf32, gifb200_stream_t stream) {
+    return tail_bwd_impl(gy, y, acc, d, gt, gacc, gb, gd, B, P, C, slope, gain, rtf32, nullptr, nullptr, stream);
+}
+
+int gifb200_tail_bwd_planes(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
+                            float* gb, float* gd, int B, int P, int C, float slope, float gain, void* gt_planes,
+                            void* gacc_planes, gifb200_stream_t stream) {
+    return tail_bwd_impl(gy, y, acc, d, gt, gacc, gb, gd, B, P, C, slope, gain, 0, gt_planes, gacc_planes, stream);
 }
 
 int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx, float* gs, int B, int P, int C, int rtf32,

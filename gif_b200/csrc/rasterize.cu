@@ -6,10 +6,11 @@
 //   1. bin_kernel<count> / bin_scan / bin_kernel<fill>: every triangle that passes the convention's face test and has a
 //      non-empty clamped bbox is appended to the list of each 16x16-pixel tile its bbox touches;
 //   2. raster_tile_kernel: one CTA per (image, tile).  The tile's depth buffer lives in SHARED memory as 64-bit keys
-//      (order-preserving depth bits << 32 | face index), initialised from the caller's depth buffer.  Threads take
-//      (list entry, row phase) pairs -- 4 lanes per triangle, rows interleaved -- do the per-triangle setup once, walk
-//      only the triangle's bbox inside the tile (the work is the number of bbox pixels, like the reference's per-triangle
-//      threads, not tile pixels x list length), and resolve depth with shared-memory atomicMin on the key: min depth
+//      (order-preserving depth bits << 32 | face index), initialised from the caller's depth buffer.  Each thread sets up
+//      one triangle of the list (once), a CTA-wide prefix sum over the clipped bbox areas flattens all fragments of the
+//      tile into one index space that the 256 threads walk evenly (the work is the number of bbox pixels, like the
+//      reference's per-triangle threads, not tile pixels x list length -- and no lane idles behind a large triangle), and
+//      depth is resolved with shared-memory atomicMin on the key: min depth
 //      wins, exact ties are won by the lowest face index, a fragment must be closer than (or tie) the caller's initial
 //      depth -- a pure function of the inputs.  After a barrier one thread per pixel re-evaluates the winner's
 //      barycentrics with the same arithmetic and writes depth / triangle / payload once, coalesced; up to two attribute
@@ -35,7 +36,6 @@
 namespace gifb200 {
 
 constexpr int TILE = 16;
-constexpr int SUB = 4;                // lanes per triangle in the tile kernel (bbox rows interleaved)
 constexpr int kNoFace = 0x7fffffff;
 constexpr float kP3dEps = 1e-8f;
 
@@ -236,8 +236,36 @@ __device__ __forceinline__ void interpolate3(const float* __restrict__ c, float 
         o[k] = __fadd_rn(__fadd_rn(__fmul_rn(b0, c[k]), __fmul_rn(b1, c[3 + k])), __fmul_rn(b2, c[6 + k]));
 }
 
+// per-face record staged in shared memory for the flattened fragment loop (16 floats: Setup0 has 13, Setup1 has 14)
+template <int CONV> struct SetupOf;
+template <> struct SetupOf<0> { using type = Setup0; };
+template <> struct SetupOf<1> { using type = Setup1; };
+
+template <int CONV>
+__device__ __forceinline__ bool eval_any(const typename SetupOf<CONV>::type& s, int x, int y, int w, int h, float& w0, float& w1,
+                                         float& w2, float& zp);
+template <>
+__device__ __forceinline__ bool eval_any<0>(const Setup0& s, int x, int y, int, int, float& w0, float& w1, float& w2, float& zp) {
+    return eval0(s, x, y, w0, w1, w2, zp);
+}
+template <>
+__device__ __forceinline__ bool eval_any<1>(const Setup1& s, int x, int y, int w, int h, float& w0, float& w1, float& w2, float& zp) {
+    return eval1(s, x, y, w, h, w0, w1, w2, zp);
+}
+template <int CONV>
+__device__ __forceinline__ typename SetupOf<CONV>::type setup_any(const float* __restrict__ fc);
+template <> __device__ __forceinline__ Setup0 setup_any<0>(const float* __restrict__ fc) { return setup0(fc); }
+template <> __device__ __forceinline__ Setup1 setup_any<1>(const float* __restrict__ fc) { return setup1(fc); }
+
 // One CTA (256 threads) per 16x16 tile.  overflow[b] != 0: this image's lists did not fit -> every CTA of the image walks
 // all F triangles (still exact).
+//
+// Phase 1 is FLATTENED: the tile's list is taken 256 triangles at a time; thread t sets up triangle t once (face test,
+// bbox clipped to the tile, edge constants) into shared memory together with its fragment count (clipped bbox area), a
+// CTA-wide prefix sum turns the counts into one index space, and every thread then takes fragments w = t, t+256, ...:
+// a binary search in the prefix array gives the triangle, the remainder the pixel.  All lanes stay busy whatever the
+// triangle sizes are (the first version gave each triangle 4 lanes that walked its bbox: ncu showed 3-4 of 32 lanes
+// active in the fragment loop and 45% of all warp samples waiting at the barrier behind the few busy warps).
 template <int CONV>
 __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
                                                           const float* __restrict__ colors2, float* __restrict__ depth,
@@ -245,12 +273,18 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
                                                           float* __restrict__ out3b, RasterGeom g,
                                                           const int* __restrict__ count, const int* __restrict__ offset,
                                                           const int* __restrict__ list, const int* __restrict__ overflow) {
+    using SetupT = typename SetupOf<CONV>::type;
     __shared__ unsigned long long key[TILE * TILE];
+    __shared__ SetupT s_setup[256];
+    __shared__ int s_incl[256];                 // inclusive prefix of the fragment counts
+    __shared__ int s_face[256];
+    __shared__ unsigned int s_box[256];         // xa | ya << 8 | width << 16  (tile-relative, all < 256)
+    __shared__ int s_warp[8];
     const int gbin = blockIdx.x;
     const int b = gbin / g.nbins, bin = gbin - b * g.nbins;
     const int by = bin / g.bins_x, bx = bin - by * g.bins_x;
     const int tx0 = bx * TILE, ty0 = by * TILE;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int px = tx0 + (t & (TILE - 1)), py = ty0 + (t >> 4);
     const bool in_img = px < g.w && py < g.h;
     const long long pix = (static_cast<long long>(b) * g.h + py) * g.w + px;
@@ -263,40 +297,65 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
         }
         key[t] = k0;
     }
-    __syncthreads();
     // phase 1: triangles -> fragments -> shared-memory depth test
     const bool brute = overflow[b] != 0;
     const int n = brute ? g.F : count[gbin];
     const int* lst = list + (brute ? 0 : offset[gbin]);
     const float* fvb = fv + static_cast<long long>(b) * g.F * 9;
-    const int sub = t & (SUB - 1);
-    for (int j = t / SUB; j < n; j += 256 / SUB) {
-        const int f = brute ? j : lst[j];
-        const float* fc = fvb + static_cast<long long>(f) * 9;
-        int xmin, xmax, ymin, ymax;
-        if (!tri_bbox<CONV>(fc, g.w, g.h, xmin, xmax, ymin, ymax)) continue;
-        const int xa = max(xmin, tx0), xb = min(xmax, tx0 + TILE - 1), ya = max(ymin, ty0), yb = min(ymax, ty0 + TILE - 1);
-        if (xa > xb || ya > yb) continue;
-        if (CONV == 0) {
-            const Setup0 s = setup0(fc);
-            for (int y = ya + sub; y <= yb; y += SUB)
-                for (int x = xa; x <= xb; ++x) {
-                    float w0, w1, w2, zp;
-                    if (!eval0(s, x, y, w0, w1, w2, zp) || !(zp == zp)) continue;
-                    const unsigned long long k = make_key(zp, f);
-                    unsigned long long* slot = &key[(y - ty0) * TILE + (x - tx0)];
-                    if (k < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, k);
+    for (int base = 0; base < n; base += 256) {
+        __syncthreads();                                 // key[] initialised / previous chunk's records consumed
+        int cnt = 0;
+        const int i = base + t;
+        if (i < n) {
+            const int f = brute ? i : lst[i];
+            const float* fc = fvb + static_cast<long long>(f) * 9;
+            int xmin, xmax, ymin, ymax;
+            if (tri_bbox<CONV>(fc, g.w, g.h, xmin, xmax, ymin, ymax)) {
+                const int xa = max(xmin, tx0), xb = min(xmax, tx0 + TILE - 1), ya = max(ymin, ty0), yb = min(ymax, ty0 + TILE - 1);
+                if (xa <= xb && ya <= yb) {
+                    s_setup[t] = setup_any<CONV>(fc);
+                    s_face[t] = f;
+                    s_box[t] = static_cast<unsigned int>(xa - tx0) | (static_cast<unsigned int>(ya - ty0) << 8) |
+                               (static_cast<unsigned int>(xb - xa + 1) << 16);
+                    cnt = (xb - xa + 1) * (yb - ya + 1);
                 }
-        } else {
-            const Setup1 s = setup1(fc);
-            for (int y = ya + sub; y <= yb; y += SUB)
-                for (int x = xa; x <= xb; ++x) {
-                    float w0, w1, w2, zp;
-                    if (!eval1(s, x, y, g.w, g.h, w0, w1, w2, zp) || !(zp == zp)) continue;
-                    const unsigned long long k = make_key(zp, f);
-                    unsigned long long* slot = &key[(y - ty0) * TILE + (x - tx0)];
-                    if (k < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, k);
-                }
+            }
+        }
+        int incl = cnt;                                   // CTA-wide inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int v = s_warp[k];
+            if (k < wid) woff += v;
+            total += v;
+        }
+        s_incl[t] = incl + woff;
+        __syncthreads();
+        for (int wk = t; wk < total; wk += 256) {
+            int lo = 0, hi = 255;                         // first record whose inclusive prefix exceeds wk
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int mid = (lo + hi) >> 1;
+                if (s_incl[mid] > wk) hi = mid; else lo = mid + 1;
+            }
+            const int r = lo;
+            const unsigned int box = s_box[r];
+            const int wd = static_cast<int>(box >> 16);
+            const int local = wk - (r ? s_incl[r - 1] : 0);
+            const int ry = local / wd, rx = local - ry * wd;
+            const int lx = static_cast<int>(box & 255u) + rx, ly = static_cast<int>((box >> 8) & 255u) + ry;
+            float w0, w1, w2, zp;
+            if (!eval_any<CONV>(s_setup[r], tx0 + lx, ty0 + ly, g.w, g.h, w0, w1, w2, zp) || !(zp == zp)) continue;
+            const unsigned long long k = make_key(zp, s_face[r]);
+            unsigned long long* slot = &key[ly * TILE + lx];
+            if (k < *reinterpret_cast<volatile unsigned long long*>(slot)) atomicMin(slot, k);
         }
     }
     __syncthreads();
@@ -306,8 +365,10 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
     if (f == kNoFace || key[t] == 0ull) return;
     const float* fc = fvb + static_cast<long long>(f) * 9;
     float w0, w1, w2, zp;
-    if (CONV == 0) { const Setup0 s = setup0(fc); eval0(s, px, py, w0, w1, w2, zp); }
-    else { const Setup1 s = setup1(fc); eval1(s, px, py, g.w, g.h, w0, w1, w2, zp); }
+    {
+        const SetupT sw = setup_any<CONV>(fc);
+        eval_any<CONV>(sw, px, py, g.w, g.h, w0, w1, w2, zp);
+    }
     depth[pix] = zp;
     tri[pix] = f;
     if (out3) {
@@ -319,87 +380,20 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-// Analytic derivatives of the winner's barycentrics / depth / attribute interpolation w.r.t. the face's vertices and
-// attributes, accumulated in registers by the thread that owns the face.
-struct FaceGrad {
-    float fv[9], c1[9], c2[9];
+// One thread per triangle gathers the pixels it owns (triangle buffer == its index) over its bbox.  The barycentrics of a
+// triangle are AFFINE in the pixel position q, so every term of the chain rule is linear in the moments
+//     M[c][m] = sum_{owned pixels} g_c(pixel) * (1, q.x, q.y)[m]
+// of the upstream gradients g_c (3 barycentric / 3 + 3 interpolated-attribute channels, and the depth term).  The pixel loop
+// therefore only accumulates moments (a few FMAs per owned pixel: lanes of a warp hit their owned pixels at different
+// iterations, so whatever sits inside the loop runs at a few active lanes), and the per-triangle algebra -- reciprocals,
+// the gradients of the dot products / edge functions -- runs ONCE per triangle after the loop at full lane occupancy.
+// No atomics, outputs are written (not accumulated), summation order is fixed: deterministic.
+struct Moments {
+    float b[3][3];      // upstream gradient of the barycentric buffer (or zero)
+    float c1[3][3];     // upstream gradient of attribute image 1, channel k
+    float c2[3][3];     // upstream gradient of attribute image 2
+    float z[3];         // depth term: sum gz * (1, q.x, q.y), gz = upstream depth gradient times d(depth)/d(s) (conv. 0) or 1
 };
-
-__device__ __forceinline__ void bwd_pixel0(const float* __restrict__ fc, int px, int py, float gw0, float gw1, float gw2, float gz_up,
-                                           bool has_depth, FaceGrad& a, float& w0o, float& w1o, float& w2o) {
-    const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
-    const float v0x = x2 - x0, v0y = y2 - y0, v1x = x1 - x0, v1y = y1 - y0, v2x = px - x0, v2y = py - y0;
-    const float d00 = v0x * v0x + v0y * v0y, d01 = v0x * v1x + v0y * v1y, d02 = v0x * v2x + v0y * v2y;
-    const float d11 = v1x * v1x + v1y * v1y, d12 = v1x * v2x + v1y * v2y;
-    const float den = d00 * d11 - d01 * d01;
-    const float inv = den == 0.f ? 0.f : 1.f / den;
-    const float nu = d11 * d02 - d01 * d12, nv = d00 * d12 - d01 * d02;
-    const float u = nu * inv, v = nv * inv;
-    const float w0 = 1.f - u - v, w1 = v, w2 = u;
-    w0o = w0; w1o = w1; w2o = w2;
-    if (has_depth) {
-        const float s = w0 / z0 + w1 / z1 + w2 / z2;
-        const float zp = 1.f / s;
-        const float gz = gz_up * (-zp * zp);   // d zp / d s
-        gw0 += gz / z0; gw1 += gz / z1; gw2 += gz / z2;
-        a.fv[2] += gz * (-w0 / (z0 * z0));
-        a.fv[5] += gz * (-w1 / (z1 * z1));
-        a.fv[8] += gz * (-w2 / (z2 * z2));
-    }
-    // (w0,w1,w2) = (1-u-v, v, u)  ->  gu = gw2 - gw0, gv = gw1 - gw0
-    const float gu = gw2 - gw0, gv = gw1 - gw0;
-    const float g_nu = gu * inv, g_nv = gv * inv;
-    const float g_den = den == 0.f ? 0.f : -(gu * nu + gv * nv) * inv * inv;
-    const float g_d00 = g_nv * d12 + g_den * d11;
-    const float g_d11 = g_nu * d02 + g_den * d00;
-    const float g_d01 = -g_nu * d12 - g_nv * d02 - 2.f * g_den * d01;
-    const float g_d02 = g_nu * d11 - g_nv * d01;
-    const float g_d12 = -g_nu * d01 + g_nv * d00;
-    const float g_v0x = 2.f * g_d00 * v0x + g_d01 * v1x + g_d02 * v2x;
-    const float g_v0y = 2.f * g_d00 * v0y + g_d01 * v1y + g_d02 * v2y;
-    const float g_v1x = 2.f * g_d11 * v1x + g_d01 * v0x + g_d12 * v2x;
-    const float g_v1y = 2.f * g_d11 * v1y + g_d01 * v0y + g_d12 * v2y;
-    const float g_v2x = g_d02 * v0x + g_d12 * v1x;
-    const float g_v2y = g_d02 * v0y + g_d12 * v1y;
-    // v0 = p2-p0, v1 = p1-p0, v2 = p-p0
-    a.fv[0] += -(g_v0x + g_v1x + g_v2x);
-    a.fv[1] += -(g_v0y + g_v1y + g_v2y);
-    a.fv[3] += g_v1x;
-    a.fv[4] += g_v1y;
-    a.fv[6] += g_v0x;
-    a.fv[7] += g_v0y;
-}
-
-// convention 1: w_i = E_i(p) / A with E_0 = E(p,v1,v2), E_1 = E(p,v2,v0), E_2 = E(p,v0,v1), A = E(v2,v0,v1) + eps; pz = sum w_i z_i
-__device__ __forceinline__ void bwd_pixel1(const float* __restrict__ fc, int px, int py, int w, int h, float gw0, float gw1, float gw2,
-                                           float gz_up, bool has_depth, FaceGrad& a, float& w0o, float& w1o, float& w2o) {
-    const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
-    const float xf = -1.f + (2 * (w - 1 - px) + 1.0f) / w, yf = -1.f + (2 * (h - 1 - py) + 1.0f) / h;
-    const float A = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + kP3dEps;
-    const float e0 = (xf - x1) * (y2 - y1) - (yf - y1) * (x2 - x1);
-    const float e1 = (xf - x2) * (y0 - y2) - (yf - y2) * (x0 - x2);
-    const float e2 = (xf - x0) * (y1 - y0) - (yf - y0) * (x1 - x0);
-    const float iA = 1.f / A;
-    const float w0 = e0 * iA, w1 = e1 * iA, w2 = e2 * iA;
-    w0o = w0; w1o = w1; w2o = w2;
-    if (has_depth) {        // pz = w0 z0 + w1 z1 + w2 z2
-        gw0 += gz_up * z0; gw1 += gz_up * z1; gw2 += gz_up * z2;
-        a.fv[2] += gz_up * w0; a.fv[5] += gz_up * w1; a.fv[8] += gz_up * w2;
-    }
-    const float ge0 = gw0 * iA, ge1 = gw1 * iA, ge2 = gw2 * iA;
-    const float gA = -(gw0 * e0 + gw1 * e1 + gw2 * e2) * iA * iA;
-    // E(p,a,b): dE/da = (p.y - b.y, b.x - p.x), dE/db = (-(p.y - a.y), p.x - a.x)
-    // e0 = E(p, v1, v2)
-    a.fv[3] += ge0 * (yf - y2); a.fv[4] += ge0 * (x2 - xf); a.fv[6] += ge0 * -(yf - y1); a.fv[7] += ge0 * (xf - x1);
-    // e1 = E(p, v2, v0)
-    a.fv[6] += ge1 * (yf - y0); a.fv[7] += ge1 * (x0 - xf); a.fv[0] += ge1 * -(yf - y2); a.fv[1] += ge1 * (xf - x2);
-    // e2 = E(p, v0, v1)
-    a.fv[0] += ge2 * (yf - y1); a.fv[1] += ge2 * (x1 - xf); a.fv[3] += ge2 * -(yf - y0); a.fv[4] += ge2 * (xf - x0);
-    // A = E(v2, v0, v1) + eps: "p" = v2, a = v0, b = v1
-    a.fv[6] += gA * (y1 - y0); a.fv[7] += gA * -(x1 - x0);
-    a.fv[0] += gA * (y2 - y1); a.fv[1] += gA * (x1 - x2);
-    a.fv[3] += gA * -(y2 - y0); a.fv[4] += gA * (x2 - x0);
-}
 
 template <int CONV>
 __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
@@ -413,9 +407,29 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
     const int b = static_cast<int>(i / F), f = static_cast<int>(i - static_cast<long long>(b) * F);
     const long long fo = i * 9;
     const float* fc = fv + fo;
-    FaceGrad a;
+    const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
+    Moments M;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { a.fv[k] = 0.f; a.c1[k] = 0.f; a.c2[k] = 0.f; }
+    for (int a = 0; a < 3; ++a) {
+        M.z[a] = 0.f;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { M.b[a][m] = 0.f; M.c1[a][m] = 0.f; M.c2[a][m] = 0.f; }
+    }
+    const bool use1 = g_img && colors, use2 = g_img2 && colors2;
+    // affine form of the barycentrics: convention 0: u = Ux qx + Uy qy, v = Vx qx + Vy qy with q = p - p0
+    //                                  convention 1: w_i = (k_i0 + k_ix qx + k_iy qy) / A with q = NDC pixel centre
+    float Ux = 0.f, Uy = 0.f, Vx = 0.f, Vy = 0.f, inv = 0.f, d00 = 0.f, d01 = 0.f, d11 = 0.f;
+    const float v0x = x2 - x0, v0y = y2 - y0, v1x = x1 - x0, v1y = y1 - y0;
+    float A = 1.f;
+    if (CONV == 0) {
+        d00 = v0x * v0x + v0y * v0y; d01 = v0x * v1x + v0y * v1y; d11 = v1x * v1x + v1y * v1y;
+        const float den = d00 * d11 - d01 * d01;
+        inv = den == 0.f ? 0.f : 1.f / den;
+        Ux = inv * (d11 * v0x - d01 * v1x); Uy = inv * (d11 * v0y - d01 * v1y);
+        Vx = inv * (d00 * v1x - d01 * v0x); Vy = inv * (d00 * v1y - d01 * v0y);
+    } else {
+        A = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + kP3dEps;
+    }
     int xmin, xmax, ymin, ymax;
     if (tri_bbox<CONV>(fc, w, h, xmin, xmax, ymin, ymax)) {
         const long long img = static_cast<long long>(b) * h * w;
@@ -423,43 +437,132 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
             for (int x = xmin; x <= xmax; ++x) {
                 const long long pix = img + static_cast<long long>(y) * w + x;
                 if (tri[pix] != f) continue;
-                float gw0 = 0.f, gw1 = 0.f, gw2 = 0.f;
-                if (g_bary) { gw0 = g_bary[pix * 3]; gw1 = g_bary[pix * 3 + 1]; gw2 = g_bary[pix * 3 + 2]; }
-                float gi[3] = {0.f, 0.f, 0.f}, gi2[3] = {0.f, 0.f, 0.f};
-                if (g_img && colors) {
-                    const float* c = colors + fo;
+                float qx, qy;
+                if (CONV == 0) { qx = x - x0; qy = y - y0; }
+                else { qx = -1.f + (2 * (w - 1 - x) + 1.0f) / w; qy = -1.f + (2 * (h - 1 - y) + 1.0f) / h; }
+                if (g_bary) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        gi[k] = g_img[pix * 3 + k];
-                        gw0 += gi[k] * c[k]; gw1 += gi[k] * c[3 + k]; gw2 += gi[k] * c[6 + k];
+                    for (int a = 0; a < 3; ++a) {
+                        const float g = g_bary[pix * 3 + a];
+                        M.b[a][0] += g; M.b[a][1] += g * qx; M.b[a][2] += g * qy;
                     }
                 }
-                if (g_img2 && colors2) {
-                    const float* c = colors2 + fo;
+                if (use1) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        gi2[k] = g_img2[pix * 3 + k];
-                        gw0 += gi2[k] * c[k]; gw1 += gi2[k] * c[3 + k]; gw2 += gi2[k] * c[6 + k];
+                        const float g = g_img[pix * 3 + k];
+                        M.c1[k][0] += g; M.c1[k][1] += g * qx; M.c1[k][2] += g * qy;
                     }
                 }
-                float w0, w1, w2;
-                if (CONV == 0) bwd_pixel0(fc, x, y, gw0, gw1, gw2, g_depth ? g_depth[pix] : 0.f, g_depth != nullptr, a, w0, w1, w2);
-                else bwd_pixel1(fc, x, y, w, h, gw0, gw1, gw2, g_depth ? g_depth[pix] : 0.f, g_depth != nullptr, a, w0, w1, w2);
+                if (use2) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    a.c1[k] += gi[k] * w0; a.c1[3 + k] += gi[k] * w1; a.c1[6 + k] += gi[k] * w2;
-                    a.c2[k] += gi2[k] * w0; a.c2[3 + k] += gi2[k] * w1; a.c2[6 + k] += gi2[k] * w2;
+                    for (int k = 0; k < 3; ++k) {
+                        const float g = g_img2[pix * 3 + k];
+                        M.c2[k][0] += g; M.c2[k][1] += g * qx; M.c2[k][2] += g * qy;
+                    }
+                }
+                if (g_depth) {
+                    float gz = g_depth[pix];
+                    if (CONV == 0) {          // zp = 1 / s, s = sum w_i / z_i: the factor d zp / d s = -zp^2 needs this pixel's weights
+                        const float u = Ux * qx + Uy * qy, v = Vx * qx + Vy * qy;
+                        const float sden = (1.f - u - v) / z0 + v / z1 + u / z2;
+                        const float zp = 1.f / sden;
+                        gz *= -zp * zp;
+                    }
+                    M.z[0] += gz; M.z[1] += gz * qx; M.z[2] += gz * qy;
                 }
             }
     }
+    // ---- per-triangle algebra.  Gw[i][m]: moments of the total upstream gradient of barycentric i
+    float Gw[3][3];
+    const float* c = colors ? colors + fo : nullptr;
+    const float* c2 = colors2 ? colors2 + fo : nullptr;
+    const float zi[3] = {z0, z1, z2};
 #pragma unroll
-    for (int k = 0; k < 9; ++k) g_fv[fo + k] = a.fv[k];
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            float t = M.b[a][m];
+            if (use1) t += M.c1[0][m] * c[a * 3 + 0] + M.c1[1][m] * c[a * 3 + 1] + M.c1[2][m] * c[a * 3 + 2];
+            if (use2) t += M.c2[0][m] * c2[a * 3 + 0] + M.c2[1][m] * c2[a * 3 + 1] + M.c2[2][m] * c2[a * 3 + 2];
+            if (g_depth) t += (CONV == 0 ? M.z[m] / zi[a] : M.z[m] * zi[a]);     // d s / d w_i = 1/z_i   |   d pz / d w_i = z_i
+            Gw[a][m] = t;
+        }
+    float gf[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gf[k] = 0.f;
+    float Wz[3] = {0.f, 0.f, 0.f};          // sum gz * w_i  (depth gradient w.r.t. the vertex depths)
+    float gc1[9], gc2[9];
+    if (CONV == 0) {
+        // (w0, w1, w2) = (1-u-v, v, u): Su = moments of (gw2 - gw0), Sv = moments of (gw1 - gw0)
+        float Su[3], Sv[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { Su[m] = Gw[2][m] - Gw[0][m]; Sv[m] = Gw[1][m] - Gw[0][m]; }
+        const float Au02 = v0x * Su[1] + v0y * Su[2], Au12 = v1x * Su[1] + v1y * Su[2];
+        const float Av02 = v0x * Sv[1] + v0y * Sv[2], Av12 = v1x * Sv[1] + v1y * Sv[2];
+        const float Gden = -((d11 * Au02 - d01 * Au12) + (d00 * Av12 - d01 * Av02)) * inv * inv;   // inv == 0 for den == 0
+        const float g_d00 = inv * Av12 + Gden * d11;
+        const float g_d11 = inv * Au02 + Gden * d00;
+        const float g_d01 = -inv * Au12 - inv * Av02 - 2.f * Gden * d01;
+        float Sd02[3], Sd12[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { Sd02[m] = inv * (d11 * Su[m] - d01 * Sv[m]); Sd12[m] = inv * (-d01 * Su[m] + d00 * Sv[m]); }
+        const float g_v0x = 2.f * g_d00 * v0x + g_d01 * v1x + Sd02[1], g_v0y = 2.f * g_d00 * v0y + g_d01 * v1y + Sd02[2];
+        const float g_v1x = 2.f * g_d11 * v1x + g_d01 * v0x + Sd12[1], g_v1y = 2.f * g_d11 * v1y + g_d01 * v0y + Sd12[2];
+        const float g_v2x = Sd02[0] * v0x + Sd12[0] * v1x, g_v2y = Sd02[0] * v0y + Sd12[0] * v1y;
+        gf[0] = -(g_v0x + g_v1x + g_v2x); gf[1] = -(g_v0y + g_v1y + g_v2y);   // v0 = p2-p0, v1 = p1-p0, v2 = p-p0
+        gf[3] = g_v1x; gf[4] = g_v1y; gf[6] = g_v0x; gf[7] = g_v0y;
+        // sums of g * w_i with w2 = u = Ux qx + Uy qy, w1 = v = Vx qx + Vy qy, w0 = 1 - u - v
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float a2 = Ux * M.c1[k][1] + Uy * M.c1[k][2], a1 = Vx * M.c1[k][1] + Vy * M.c1[k][2];
+            gc1[6 + k] = a2; gc1[3 + k] = a1; gc1[k] = M.c1[k][0] - a1 - a2;
+            const float b2 = Ux * M.c2[k][1] + Uy * M.c2[k][2], b1 = Vx * M.c2[k][1] + Vy * M.c2[k][2];
+            gc2[6 + k] = b2; gc2[3 + k] = b1; gc2[k] = M.c2[k][0] - b1 - b2;
+        }
+        Wz[2] = Ux * M.z[1] + Uy * M.z[2]; Wz[1] = Vx * M.z[1] + Vy * M.z[2]; Wz[0] = M.z[0] - Wz[1] - Wz[2];
+        if (g_depth) { gf[2] = -Wz[0] / (z0 * z0); gf[5] = -Wz[1] / (z1 * z1); gf[8] = -Wz[2] / (z2 * z2); }   // d s / d z_i = -w_i / z_i^2
+    } else {
+        // e_0 = E(q,v1,v2), e_1 = E(q,v2,v0), e_2 = E(q,v0,v1), E(q,a,b) = (qx-ax)(by-ay) - (qy-ay)(bx-ax); w_i = e_i / A
+        const float iA = 1.f / A;
+        const float ax[3] = {x1, x2, x0}, ay[3] = {y1, y2, y0}, bx[3] = {x2, x0, x1}, by[3] = {y2, y0, y1};
+        const int ia[3] = {1, 2, 0}, ib[3] = {2, 0, 1};       // vertex index of a and b for e_i
+        float sum_ge = 0.f;                                    // sum_i sum_pix gw_i e_i
+        float ki[3][3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const float dyb = by[e] - ay[e], dxb = bx[e] - ax[e];
+            ki[e][0] = -ax[e] * dyb + ay[e] * dxb; ki[e][1] = dyb; ki[e][2] = -dxb;        // e = k0 + k1 qx + k2 qy
+            sum_ge += ki[e][0] * Gw[e][0] + ki[e][1] * Gw[e][1] + ki[e][2] * Gw[e][2];
+            // dE/da = (q.y - b.y, b.x - q.x), dE/db = (-(q.y - a.y), q.x - a.x), summed over the pixels with weight gw_e / A
+            const float g0 = Gw[e][0] * iA, gx_ = Gw[e][1] * iA, gy_ = Gw[e][2] * iA;
+            gf[ia[e] * 3 + 0] += gy_ - by[e] * g0; gf[ia[e] * 3 + 1] += bx[e] * g0 - gx_;
+            gf[ib[e] * 3 + 0] += -(gy_ - ay[e] * g0); gf[ib[e] * 3 + 1] += gx_ - ax[e] * g0;
+        }
+        const float gA = -sum_ge * iA * iA;
+        // A = E(v2, v0, v1) + eps: "q" = v2, a = v0, b = v1
+        gf[6] += gA * (y1 - y0); gf[7] += gA * -(x1 - x0);
+        gf[0] += gA * (y2 - y1); gf[1] += gA * (x1 - x2);
+        gf[3] += gA * -(y2 - y0); gf[4] += gA * (x2 - x0);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                gc1[e * 3 + k] = (ki[e][0] * M.c1[k][0] + ki[e][1] * M.c1[k][1] + ki[e][2] * M.c1[k][2]) * iA;
+                gc2[e * 3 + k] = (ki[e][0] * M.c2[k][0] + ki[e][1] * M.c2[k][1] + ki[e][2] * M.c2[k][2]) * iA;
+            }
+            Wz[e] = (ki[e][0] * M.z[0] + ki[e][1] * M.z[1] + ki[e][2] * M.z[2]) * iA;
+        }
+        if (g_depth) { gf[2] = Wz[0]; gf[5] = Wz[1]; gf[8] = Wz[2]; }          // pz = sum w_i z_i
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g_fv[fo + k] = gf[k];
     if (g_col)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) g_col[fo + k] = a.c1[k];
+        for (int k = 0; k < 9; ++k) g_col[fo + k] = use1 ? gc1[k] : 0.f;
     if (g_col2)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) g_col2[fo + k] = a.c2[k];
+        for (int k = 0; k < 9; ++k) g_col2[fo + k] = use2 ? gc2[k] : 0.f;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -37,12 +37,13 @@ def init_from_env(backend=None):
 class FlatGradAllReducer:
     """Gradient exchange for one network: a flat fp32 buffer with one slot per parameter that can receive a gradient.
 
-    ``attach()`` (called once, and again by ``zero()`` only if autograd replaced a ``.grad``) makes every parameter's
-    ``.grad`` a view into the flat buffer, so backward accumulates straight into it and the exchange is ONE collective
-    with no gather pass.  ``pre_scale()`` returns the 1/world factor to fold into the loss (so that the SUM all-reduce
-    already yields the mean and no separate scaling pass runs); ``all_reduce_mean()`` keeps the classic "sum then scale"
-    semantics for callers that did not pre-scale.  ``bucket_bytes`` splits the buffer into a few contiguous chunks issued
-    back to back as asynchronous collectives (they pipeline inside NCCL; the last one is waited on)."""
+    Per step: ``zero()`` clears every ``.grad`` (sets it to None -- no memset, and autograd then MOVES each freshly computed
+    gradient into ``.grad`` instead of launching one ``grad += new`` kernel per parameter: ~500 launches and two full
+    read-modify-write passes over the gradients per iteration in round 1); ``all_reduce_sum()`` packs the gradients into
+    the flat buffer with one multi-tensor copy, runs ONE collective (or a few contiguous buckets, issued back to back),
+    and points every ``.grad`` at its slot.  With one rank nothing is packed at all: the optimiser reads the gradients
+    where autograd left them, and parameters that were not used keep ``grad = None`` exactly as in the reference.
+    ``pre_scale()`` is the 1/world factor to fold into the loss so that the SUM already yields the mean."""
 
     def __init__(self, params, world_size=None, group=None, bucket_bytes=None):
         self.params = [p for p in params]
@@ -59,46 +60,59 @@ class FlatGradAllReducer:
         self.nbytes = n * 4
         per = n if not bucket_bytes else max(1, int(bucket_bytes) // 4)
         self.buckets = [self.flat[a:min(a + per, n)] for a in range(0, max(n, 1), per)] if n else []
-        self._attached = False
+        self._dirty = [False] * len(self.params)
 
     def attach(self):
-        """Make every parameter's .grad a view into the flat buffer (so backward accumulates straight into it)."""
+        """Make every parameter's .grad a view into the (zeroed) flat buffer: backward then accumulates straight into it.
+        The round-1 scheme; kept for callers that want in-place accumulation across several backward calls."""
+        self.flat.zero_()
+        self._dirty = [True] * len(self.params)
         for p, v in zip(self.params, self.views):
             p.grad = v
-        self._attached = True
-
-    def _reattach_strays(self):
-        """Parameters whose .grad was replaced (autograd assigns a fresh tensor when .grad was None; optimizer.zero_grad
-        sets None): copy what they hold into the slot and point them back at it.  A no-op walk of pointer compares on the
-        steady-state path (nothing strays once attached)."""
-        for p, v in zip(self.params, self.views):
-            g = p.grad
-            if g is None:
-                p.grad = v
-            elif g.data_ptr() != v.data_ptr():
-                v.copy_(g)
-                p.grad = v
 
     def zero(self):
-        self.flat.zero_()
-        if not self._attached:
-            self.attach()
-        else:
-            for p, v in zip(self.params, self.views):      # parameters unused in this step keep a zero gradient
-                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                    p.grad = v
+        for p in self.params:
+            p.grad = None
 
     def pre_scale(self):
         """Factor to multiply the local loss by so that ``all_reduce_sum()`` leaves the MEAN gradient in the buffer."""
         return 1.0 / self.world
 
+    def pack(self):
+        """Gather the gradients autograd produced into their slots (one multi-tensor copy) and point every ``.grad`` at its
+        slot; parameters without a gradient on this rank contribute zeros (another rank may have used them); gradients
+        that already live in their slot (after ``attach()``) are left alone.  Stream-ordered device work only, so it can
+        be the tail of a captured CUDA graph (the collective itself stays outside).  A no-op with a single rank."""
+        if self.world <= 1:
+            return
+        src, dst = [], []
+        for i, (p, v) in enumerate(zip(self.params, self.views)):
+            g = p.grad
+            if g is None:
+                if self._dirty[i]:                       # slots start zeroed and stay zero until a gradient is copied in
+                    v.zero_()
+                    self._dirty[i] = False
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g)
+                dst.append(v)
+                self._dirty[i] = True
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def reduce(self):
+        """The collective on the packed buffer: SUM over ranks, in place (bucketed).  A no-op with a single rank."""
+        if self.world <= 1:
+            return
+        works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
+        for w in works:
+            w.wait()
+
     def all_reduce_sum(self):
-        """SUM over ranks, in place, bucketed.  Use with a loss pre-scaled by ``pre_scale()``."""
-        self._reattach_strays()
-        if self.world > 1:
-            works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for b in self.buckets]
-            for w in works:
-                w.wait()
+        """pack() + reduce().  Use with a loss pre-scaled by ``pre_scale()``."""
+        self.pack()
+        self.reduce()
 
     def all_reduce_mean(self):
         """SUM over ranks then 1/world (for losses that were not pre-scaled)."""
@@ -138,10 +152,9 @@ def _optimizer_pre_step_hook(optimizer, args, kwargs):
     if red is None or len(red.params) != len(params) or any(a is not b for a, b in zip(red.params, params)):
         red = FlatGradAllReducer(params, dist.get_world_size())
         _reducers[id(optimizer)] = red
-    for p, v in zip(params, red.views):
-        if p.grad is None:                     # e.g. the unused high-resolution blocks (gen.py:175): zeros from this rank.
-            v.zero_()                          # Adam's update for an all-zero gradient is exactly 0 (0 / (0 + eps))
-    red.all_reduce_mean()                      # strays are copied into their slots first
+    # parameters without a gradient here (e.g. the unused high-resolution blocks, gen.py:175) contribute zeros; Adam's
+    # update for an all-zero gradient is exactly 0 (0 / (0 + eps))
+    red.all_reduce_mean()
     return None
 
 

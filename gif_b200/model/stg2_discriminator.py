@@ -54,7 +54,7 @@ class Discriminator(nn.Module):
             input = input[0]
         if condition is not None:
             input = torch.cat((input, condition), axis=1)                 # disc.py:53 (9 channels)
-        x = ops.to_nhwc(input)
+        x = ops.from_reference_nchw(input)           # gradients w.r.t. the caller's images come back NCHW-contiguous
         x = self.convs[0].forward_nhwc(x, rt_out=True)
         for block in list(self.convs)[1:]:
             x = block.forward_nhwc(x)

@@ -229,15 +229,15 @@ class ModulatedConv2d(nn.Module):
             # ToRGB: per-sample 1x1 weights ws[b,c,i] = W~[c,i] s[b,i] (3*Ci numbers per sample), no modulated copy of x
             acc = ops.torgb(x, wt[0][None] * s[:, None, :])
         else:
-            xs = ops.chan_scale(x, s, ops.tf32_enabled())
             if self.upsample:
-                acc = ops.conv2d(xs, wt, k, ops.T2)                       # (2H+1)^2  cl.py:322-331
+                acc = ops.modconv(x, s, wt, k, ops.T2)                    # (2H+1)^2  cl.py:322-331
                 acc = ops.upfirdn2d(acc, self.blur.kernel, pad=self.blur.pad)   # cl.py:333
             elif self.downsample:
+                xs = ops.chan_scale(x, s, ops.tf32_enabled())
                 xs = ops.upfirdn2d(xs, self.blur.kernel, pad=self.blur.pad, rt=ops.tf32_enabled())
                 acc = ops.conv2d(xs, wt, k, ops.S2)                       # cl.py:335-341
             else:
-                acc = ops.conv2d(xs, wt, k, ops.S1)                       # cl.py:343-347
+                acc = ops.modconv(x, s, wt, k, ops.S1)                    # cl.py:343-347
         d = None
         if self.demodulate:
             q = (wt * wt).sum(dim=0)                                      # (Co,Ci) = sum_taps W~^2

@@ -122,8 +122,9 @@ def conv_out_size(hi, k, mode):
     return 2 * (hi - 1) + k
 
 
-def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None):
-    """epilogue: None (plain accumulator) or (bias_flat or None, slope, gain, round_tf32) fused into the kernel."""
+def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None, planes=None):
+    """epilogue: None (plain accumulator) or (bias_flat or None, slope, gain, round_tf32) fused into the kernel.
+    planes: the bf16x3 operand of the INPUT when the caller already has it (x then only supplies shape and device)."""
     require_cuda(x, w)
     B, Hi, Wi, Ci = x.shape
     T, R, S = w.shape
@@ -135,7 +136,7 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None):
     impl, xin = CONV_IMPL, x
     if CONV_IMPL == 3:
         if nws > 0:
-            xin = _planes(x)                 # compensated tensor-core path: the kernel reads the split planes
+            xin = planes if planes is not None else _planes(x)   # compensated tensor-core path: the kernel reads the split planes
         else:
             impl = 1                         # shape outside the tensor-core path: exact fp32 SIMT
     elif nws > 0 and not _is_tf32(x):        # tensor-core path: operands must be tf32-representable (see gifb200.h)
@@ -161,7 +162,7 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None):
     return y, x
 
 
-def _wgrad_raw(x, gy, k, mode, flip, transposed):
+def _wgrad_raw(x, gy, k, mode, flip, transposed, x_planes=None):
     require_cuda(x, gy)
     B, Hi, Wi, Ci = x.shape
     _, Ho, Wo, Co = gy.shape
@@ -171,7 +172,7 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
     path = lib.gifb200_conv2d_wgrad_path(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, impl)
     xin, gin = x, gy
     if path == 3:                              # compensated contraction on the split planes of both operands
-        xin, gin = _planes(x), _planes(gy)
+        xin, gin = (x_planes if x_planes is not None else _planes(x)), _planes(gy)
     elif path == 2:                            # MN-major kind::tf32 path: operands must be tf32-representable
         if not _is_tf32(x):
             xin = _round_tf32_raw(x)
@@ -192,6 +193,26 @@ def _wgrad_raw(x, gy, k, mode, flip, transposed):
         pix = Hi * Wi if mode == T2 else Ho * Wo
         PROFILE.append((ev0, ev1, 2.0 * B * pix * Ci * Co * k * k, "wgrad", ("wgrad", mode, B, Hi, Wi, Ci, Co, k)))
     return gw
+
+
+def _x3_backward_on_planes(x_shape, gy_shape, k, mode):
+    """True when, in bf16x3 mode, BOTH consumers of a convolution's output gradient -- the input-gradient convolution and the
+    weight gradient -- run on the tensor cores for these shapes, i.e. read only the split planes of gy (never its fp32 form)."""
+    if CONV_IMPL != 3:
+        return False
+    B, Hi, Wi, Ci = x_shape
+    _, Ho, Wo, Co = gy_shape
+    if lib.gifb200_conv2d_workspace_bytes(B, Ho, Wo, Co, Hi, Wi, Ci, k, _ADJ_MODE[mode], 1, 3) == 0:
+        return False
+    return lib.gifb200_conv2d_wgrad_path(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, 3) == 3
+
+
+def _planes_carrier(like, planes):
+    """A gradient whose values exist ONLY as bf16x3 planes: an unwritten fp32 tensor of the right shape carrying them.  Used
+    strictly between a fused backward kernel and the two tensor-core contractions that consume it (_x3_backward_on_planes)."""
+    t = torch.empty_like(like)
+    t._gifb200_planes = (t._version, planes)
+    return t
 
 
 class _Conv(torch.autograd.Function):
@@ -277,8 +298,15 @@ class _ConvBiasAct(torch.autograd.Function):
             gt = torch.empty_like(gy)
             want_b = bias_shape is not None and ctx.needs_input_grad[2]
             gbf = torch.empty(C, dtype=torch.float32, device=gy.device) if want_b else None
-            check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(y), None, ptr(gt), None, ptr(gbf), None, 1, rows, C, slope, gain,
-                                       int(rt), stream()), "gifb200_tail_bwd")
+            if C % 32 == 0 and _x3_backward_on_planes(x.shape, gy.shape, k, mode):
+                # bf16x3: the activation backward writes the dgrad / wgrad operand (split planes) directly, no fp32 copy
+                pl = torch.empty((2,) + tuple(gy.shape), dtype=torch.bfloat16, device=gy.device)
+                check(lib.gifb200_tail_bwd_planes(ptr(gy), ptr(y), ptr(y), None, None, None, ptr(gbf), None, 1, rows, C, slope,
+                                                  gain, ptr(pl), None, stream()), "gifb200_tail_bwd_planes")
+                gt._gifb200_planes = (gt._version, pl)
+            else:
+                check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(y), None, ptr(gt), None, ptr(gbf), None, 1, rows, C, slope, gain,
+                                           int(rt), stream()), "gifb200_tail_bwd")
             _tag(gt, rt)
             if want_b:
                 gb = gbf.reshape(bias_shape)
@@ -387,8 +415,20 @@ class _BiasAct(torch.autograd.Function):
             want_d = rowscale is not None and ctx.needs_input_grad[1]
             gb = torch.empty(C, dtype=torch.float32, device=gy.device) if want_b else None
             gd = torch.empty((B, C), dtype=torch.float32, device=gy.device) if want_d else None
-            check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(x), ptr(rowscale), ptr(gt), ptr(gacc), ptr(gb), ptr(gd), B, P, C,
-                                       slope, gain, int(rt), stream()), "gifb200_tail_bwd")
+            if CONV_IMPL == 3 and C % 32 == 0 and P >= 256:
+                # bf16x3: the gradients leave on autograd edges towards convolutions (the modulated conv and the noise branch)
+                # or FIR filters: write the fp32 form AND the split planes in the same pass (saves the split pass's read)
+                pt = torch.empty((2,) + tuple(gy.shape), dtype=torch.bfloat16, device=gy.device) if has_add else None
+                pa = torch.empty((2,) + tuple(gy.shape), dtype=torch.bfloat16, device=gy.device) if gacc is not None else None
+                check(lib.gifb200_tail_bwd_planes(ptr(gy), ptr(y), ptr(x), ptr(rowscale), ptr(gt), ptr(gacc), ptr(gb), ptr(gd), B,
+                                                  P, C, slope, gain, ptr(pt), ptr(pa), stream()), "gifb200_tail_bwd_planes")
+                if pt is not None:
+                    gt._gifb200_planes = (gt._version, pt)
+                if pa is not None:
+                    gacc._gifb200_planes = (gacc._version, pa)
+            else:
+                check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(x), ptr(rowscale), ptr(gt), ptr(gacc), ptr(gb), ptr(gd), B, P, C,
+                                           slope, gain, int(rt), stream()), "gifb200_tail_bwd")
             _tag(gt, rt)
             if gacc is not None:
                 _tag(gacc, rt)
@@ -517,6 +557,67 @@ class _SpatialDot(torch.autograd.Function):
 
 def chan_scale(x, s, round_tf32=False):
     return _tag(_ChanScale.apply(x, s, round_tf32), round_tf32)
+
+
+class _ModConvX3(torch.autograd.Function):
+    """y = conv(x * s[b, :]; w) in the bf16x3 mode with the modulation fused into the operand split: ONE pass reads x and
+    writes the two bf16 planes of x*s (gifb200_split_bf16 with a scale vector), the tensor-core kernel reads those; the
+    fp32 modulated copy of the input (2 x 1.07 GB per 256^2 layer) never exists.  First-order backward: input-gradient
+    convolution + the fused scale_bwd pass + weight gradient on the saved planes; when a higher derivative is being recorded
+    (path-length regulariser) the backward is the closed set of differentiable ops (chan_scale, conv, wgrad, spatial_dot)."""
+
+    @staticmethod
+    def forward(ctx, x, s, w, k, mode, out_hw):
+        x, s, w = _c(x), _c(s), _c(w)
+        require_cuda(x, s, w)
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // max(B * C, 1)
+        pl = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+        check(lib.gifb200_split_bf16(ptr(x), ptr(s), ptr(pl), B, P, C, stream()), "gifb200_split_bf16(scale)")
+        y, _ = _conv_raw(x, w, k, mode, False, False, out_hw, planes=pl)
+        ctx.save_for_backward(x, s, w)
+        ctx.planes = pl
+        ctx.cfg = (k, mode, tuple(x.shape[1:3]))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s, w = ctx.saved_tensors
+        k, mode, in_hw = ctx.cfg
+        adj = (gy, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
+        if torch.is_grad_enabled():
+            xs = chan_scale(x, s)
+            gxs = _Conv.apply(*adj) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+            gx = chan_scale(gxs, s) if ctx.needs_input_grad[0] else None
+            gs = spatial_dot(gxs, x) if ctx.needs_input_grad[1] else None
+            gw = _ConvWgrad.apply(xs, gy, k, mode, False, False) if ctx.needs_input_grad[2] else None
+            return gx, gs, gw, None, None, None
+        gy = _c(gy)
+        gx = gs = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gxs, _ = _conv_raw(gy, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
+            B, C = gxs.shape[0], gxs.shape[-1]
+            P = gxs.numel() // max(B * C, 1)
+            gx = torch.empty_like(gxs)
+            gs = torch.empty((B, C), dtype=torch.float32, device=gy.device)
+            check(lib.gifb200_scale_bwd(ptr(gxs), ptr(x), ptr(s), ptr(gx), ptr(gs), B, P, C, 0, stream()), "gifb200_scale_bwd")
+        if ctx.needs_input_grad[2]:
+            gw = _wgrad_raw(x, gy, k, mode, False, False, x_planes=ctx.planes)
+        return gx, gs, gw, None, None, None
+
+
+def modconv(x, s, w, k, mode):
+    """conv(x * s; w): the modulate-input form of ModulatedConv2d (cl.py:311-347).  bf16x3 + a tensor-core shape: the fused
+    split (no modulated fp32 copy); otherwise chan_scale followed by conv2d."""
+    hi, wi = x.shape[1:3]
+    out_hw = (conv_out_size(hi, k, mode), conv_out_size(wi, k, mode))
+    if CONV_IMPL == 3 and x.shape[-1] % 4 == 0:
+        B, Ci = x.shape[0], x.shape[-1]
+        Co = w.shape[1]
+        if lib.gifb200_conv2d_workspace_bytes(B, hi, wi, Ci, out_hw[0], out_hw[1], Co, k, mode, 0, 3) > 0 and \
+                lib.gifb200_conv2d_wgrad_path(B, hi, wi, Ci, out_hw[0], out_hw[1], Co, k, mode, 3) == 3:
+            return _ModConvX3.apply(x, s, w, k, mode, out_hw)
+    return conv2d(chan_scale(x, s, tf32_enabled()), w, k, mode)
 
 
 def spatial_dot(a, b):
@@ -719,6 +820,38 @@ def cond_down(x, s):
 
 
 # --------------------------------------------------------------------------------------------- layout helpers
+class _BoundaryIn(torch.autograd.Function):
+    """NCHW tensor coming from reference-side code -> contiguous channels-last (B,H,W,C).  Same values as ``to_nhwc``; the
+    difference is the GRADIENT it hands back to the caller: contiguous in the caller's NCHW layout, as the reference's own ops
+    return it (losses.py:97 does ``grad_real.view(B, -1)`` on the R1 gradient, which a permuted view would reject)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.permute(0, 2, 3, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _BoundaryOut.apply(g)
+
+
+class _BoundaryOut(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g):
+        return g.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _BoundaryIn.apply(gg)
+
+
+def from_reference_nchw(x):
+    """Entry conversion of a module-level ``forward(input)``: see _BoundaryIn.  Free (a view) when x is already a NCHW view of
+    channels-last storage produced by this package."""
+    if x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1)
+    return _BoundaryIn.apply(x)
+
+
 def to_nhwc(x):
     """Reference-facing NCHW tensor -> contiguous (B,H,W,C).  Free when x is an NCHW *view* of one of our outputs."""
     return _c(x.permute(0, 2, 3, 1))

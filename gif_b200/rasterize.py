@@ -80,6 +80,7 @@ class _Rasterize(torch.autograd.Function):
             depth.masked_fill_(tri < 0, -1.0)
         ctx.save_for_backward(fv, fc, fc2, tri)
         ctx.mark_non_differentiable(tri)
+        ctx.set_materialize_grads(False)          # an unused output (e.g. depth) arrives as None, not as a tensor of zeros
         ctx.cfg = (h, w, convention)
         return (depth, tri, out3) if fc2 is None else (depth, tri, out3, out3b)
 

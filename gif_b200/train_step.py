@@ -144,16 +144,16 @@ class GifTrainer:
                 dst.copy_(src, non_blocking=True)
             (g1, g2, g3), out = self._graphs[with_r1]
             g1.replay()
-            self.d_reducer.all_reduce_sum()
+            self.d_reducer.reduce()                 # the pack (multi-tensor copy into the flat buffer) is the tail of graph 1
             g2.replay()
-            self.g_reducer.all_reduce_sum()
+            self.g_reducer.reduce()
             g3.replay()
             return out
         state = {}
         self._seg1(state, real_image, flm_rndr, input_indices, with_r1)
-        self.d_reducer.all_reduce_sum()
+        self.d_reducer.reduce()
         self._seg2(state, real_image, flm_rndr, input_indices, with_r1, *extra)
-        self.g_reducer.all_reduce_sum()
+        self.g_reducer.reduce()
         self._seg3(state, real_image, flm_rndr, input_indices, with_r1)
         return state["d_loss"], state["g_loss"]
 
@@ -175,6 +175,7 @@ class GifTrainer:
         d_loss = real_loss + F.softplus(fake_scores).mean()
         # 1/world folded into the backward seed: the SUM all-reduce then leaves the mean gradient (no scaling pass)
         (d_loss * self.d_reducer.pre_scale() if world_gt1(self.d_reducer) else d_loss).backward()
+        self.d_reducer.pack()                      # world > 1: gradients -> flat buffer (capturable); the collective follows
         st.update(w=w, fake=fake, d_loss=d_loss.detach())
 
     def _seg2(self, st, real_image, flm_rndr, input_indices, with_r1, flm_lbls=None):
@@ -199,6 +200,7 @@ class GifTrainer:
                 interp = interp * (0.25 * g_loss.detach() / interp.detach())
             g_loss = g_loss + interp
         (g_loss * self.g_reducer.pre_scale() if world_gt1(self.g_reducer) else g_loss).backward()
+        self.g_reducer.pack()
         st["g_loss"] = g_loss.detach()
         st.pop("fake")
         st.pop("w")

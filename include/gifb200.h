@@ -138,6 +138,13 @@ int gifb200_tail_bwd(const float* gy, const float* y, const float* acc, const fl
                      float* gd, int B, int P, int C, float slope, float gain, int round_tf32, gifb200_stream_t stream);
 int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx, float* gs, int B, int P, int C,
                       int round_tf32, gifb200_stream_t stream);
+/* gifb200_tail_bwd for the bf16x3 mode: gt_planes / gacc_planes (each may be NULL) receive the two-term bf16 expansion
+ * (the layout of gifb200_split_bf16) of gt / gacc in the SAME pass -- the operands of the convolution input-gradient and
+ * weight-gradient that follow -- and the fp32 outputs gt / gacc may then be NULL (at least one form of gt is required).
+ * C % 32 == 0. */
+int gifb200_tail_bwd_planes(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
+                            float* gb, float* gd, int B, int P, int C, float slope, float gain, void* gt_planes,
+                            void* gacc_planes, gifb200_stream_t stream);
 /* out[b,c] = sum_p a[b,p,c] * b2[b,p,c]  (gradient of chan_scale w.r.t. s). out is OVERWRITTEN. */
 int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream);
 /* y = alpha*a + beta*b (b may be NULL): residual merge (a+b)/sqrt2 of ResBlock.forward (cl.py:817-818),

@@ -9,12 +9,9 @@ Used three ways, always with the same seeded inputs and initial weights:
     the boundary test of SURVEY 8b and the loop-body parity of 8a L4 in one;
   * the same test file runs ``gif_b200.train_step.GifTrainer`` (one shared G forward, flat gradient buffers, fused Adam)
     on the same batches against the same golden.
-``train()`` reads four globals that train.py defines under ``__main__`` (g_optimizer, d_optimizer_flm, g_running,
-n_critic; train.py:322,365-382): ``run_reference_train`` sets them on the module exactly as ``__main__`` would.
+The runner that drives train() (globals it reads, synthetic loader, loop-counter start) is oracle/ref_train_runner.py.
 """
 import contextlib
-import math
-import types
 
 import numpy as np
 import torch
@@ -32,10 +29,6 @@ D_WATCH = ["convs.0.0.weight", "convs.0.1.bias", "convs.1.conv1.0.weight", "conv
            "convs.2.conv2.2.bias", "final_conv.0.weight", "final_linear.0.weight", "final_linear.1.weight", "final_linear.1.bias"]
 
 
-class StopTraining(Exception):
-    pass
-
-
 def batch(i, device="cpu"):
     """Iteration i's batch: FFHQ-shaped image in [-1,1], 6-channel condition in [-1,1], FLAME labels, identity indices."""
     real = gu.rand_uniform((BATCH, 3, RES, RES), 7000 + 4 * i)
@@ -43,62 +36,6 @@ def batch(i, device="cpu"):
     lbls = gu.randn((BATCH, 159), 7002 + 4 * i)
     idx = gu.randint(VOCAB, (BATCH,), 7003 + 4 * i)
     return real.to(device), cond.to(device), lbls.to(device), idx.to(device)
-
-
-class SyntheticDataset:
-    """What train() touches of the dataset object (train.py:120-122, :230, :269)."""
-
-    def __init__(self, on_iteration_start=None):
-        self.calls = 0
-        self.on_iteration_start = on_iteration_start
-
-    def accumulate_batches_of_flm(self, flm, pose):     # called once per iteration, after the batch was drawn
-        if self.on_iteration_start is not None:
-            self.on_iteration_start(self.calls)          # == number of COMPLETED iterations
-        self.calls += 1
-
-    def un_normalize_flame(self, x):
-        return x
-
-
-def make_args():
-    return types.SimpleNamespace(
-        embedding_vocab_size=VOCAB, gen_reg_type="None", batch={RES: BATCH}, batch_default=BATCH, debug=True,
-        lr={}, use_styled_conv_stylegan2=True, max_size=RES, init_size=RES, phase=10 ** 9, ckpt=None,
-        rendered_flame_as_condition=True, normal_maps_as_cond=True, shfld_cond_as_neg_smpl=False, embedding_reg_weight=0.0,
-        apply_texture_space_interpolation_loss=False, adaptive_interp_loss=False, use_posed_constant_input=False, run_id="t")
-
-
-def _loader(n_iters, first_i=0):
-    def sample_data(dataset, batch_size, image_sizes, debug=False):
-        assert batch_size == BATCH and image_sizes[-1] == RES
-
-        class Loader:
-            def __iter__(self):
-                def gen():
-                    for i in range(first_i, first_i + n_iters):
-                        real, cond, lbls, idx = batch(i)
-                        yield real, [cond], [lbls], idx
-                    raise StopTraining()
-                return gen()
-        return Loader()
-    return sample_data
-
-
-@contextlib.contextmanager
-def cuda_calls_are_noops_without_a_gpu():
-    """train() calls ``.cuda()`` on its batches (train.py:125-130); in the GPU-less build container those become no-ops so
-    that the unmodified function runs on the CPU."""
-    if torch.cuda.is_available():
-        yield
-        return
-    t_cuda, m_cuda = torch.Tensor.cuda, torch.nn.Module.cuda
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    try:
-        yield
-    finally:
-        torch.Tensor.cuda, torch.nn.Module.cuda = t_cuda, m_cuda
 
 
 def initial_state_dicts():
@@ -123,49 +60,18 @@ def build_networks(gen_mod, disc_mod, device):
 
 
 def run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after=(1,), first_i=0):
-    """Runs train_mod.train() for n_iters iterations.  Returns {k: snapshot} for k in snapshot_after + (n_iters,).
-    ``first_i``: the value train()'s loop counter starts from -- train.py:79 iterates ``tqdm(range(3_000_000))`` and the
-    harness supplies the ``tqdm`` stand-in, so it can hand the loop ``range(first_i, ...)``: with first_i = 15 the FIRST
-    iteration is an R1 iteration (``(i + 1) % 16 == 0``, train.py:145) of the unmodified function."""
-    with cuda_calls_are_noops_without_a_gpu():
-        return _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after, first_i)
-
-
-def _run_reference_train(train_mod, G, D, Gr, n_iters, snapshot_after, first_i):
-    from torch import nn, optim
-    generator = nn.DataParallel(G).cuda()                  # train.py:344 (the drop-in's stand-in when it is installed)
-    discriminator = nn.DataParallel(D).cuda()              # train.py:356
-    g_running = nn.DataParallel(Gr).cuda()                 # train.py:358
-    g_running.train(False)
-    g_ratio, d_ratio = 4 / 5, 16 / 17                      # train.py:365-382
-    train_mod.g_optimizer = optim.Adam(generator.module.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
-    train_mod.d_optimizer_flm = optim.Adam(discriminator.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
-    train_mod.g_running = g_running
-    train_mod.n_critic = 1                                 # train.py:322
-    train_mod.sample_data = _loader(n_iters, first_i)
+    """Runs train_mod.train() for n_iters iterations on batch(first_i), batch(first_i + 1), ...  Returns {k: snapshot} for
+    k in snapshot_after + (n_iters,).  ``first_i``: where train()'s loop counter starts (oracle/ref_train_runner.py): with
+    first_i = 15 the FIRST iteration is an R1 iteration (train.py:145) of the unmodified function."""
+    from oracle import ref_train_runner
     snaps = {}
 
-    def snap(done):
-        if done in snapshot_after or done == n_iters:
-            snaps[done] = snapshot(generator.module, discriminator.module, g_running.module,
-                                   train_mod.g_optimizer, train_mod.d_optimizer_flm)
+    def on_done(k, g, d, gr, g_opt, d_opt):
+        if (k in snapshot_after or k == n_iters) and k not in snaps:
+            snaps[k] = snapshot(g, d, gr, g_opt, d_opt)
 
-    class Bar:                                             # ``pbar = tqdm(range(...))`` then ``pbar.set_description``
-        def __init__(self, it):
-            self.it = it
-
-        def __iter__(self):
-            return iter(range(first_i, len(self.it)))
-
-        def set_description(self, *_a, **_k):
-            pass
-    train_mod.tqdm = Bar
-    dataset = SyntheticDataset(on_iteration_start=snap)
-    try:
-        train_mod.train(make_args(), dataset, generator, discriminator, None, None, 0, int(math.log2(RES)) - 2)
-    except StopTraining:
-        pass
-    snap(n_iters)
+    ref_train_runner.run(train_mod, G, D, Gr, [batch(i) for i in range(first_i, first_i + n_iters)], RES, VOCAB,
+                         first_i=first_i, on_iteration_done=on_done)
     return snaps
 
 

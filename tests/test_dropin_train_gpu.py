@@ -14,7 +14,8 @@ parameter agreement after one iteration is a statement about the SIGN of every g
 item 8).  Adam's second moment after iteration 1 is (1-beta2) g^2 -- a direct, well-conditioned check of the gradients
 (L2-relative 1e-3).  After 16 iterations the trajectories of two correct fp32 implementations drift apart by themselves;
 the golden stores the same train() run in float64 beside the float32 one and the bar of every tensor is 3x the
-reference's own fp32-vs-fp64 deviation for that tensor (at least 1e-3; 2e-2 for the moments)."""
+reference's own fp32-vs-fp64 deviation for that tensor after one iteration, 5x after sixteen (at least 1e-3; 2e-2 for the
+moments)."""
 import os
 import sys
 
@@ -41,7 +42,9 @@ def _bars(g, it):
 
 def _check(snaps, g, what, scenario=""):
     for it, snap in snaps.items():
-        worst, bad = H.compare(snap, g, it, scenario=scenario, **_bars(g, it))
+        # after 16 chaotic Adam steps a 1-element tensor is ONE sample of the drift distribution: 5x the reference's own
+        # fp32-vs-fp64 deviation there, 3x after a single iteration
+        worst, bad = H.compare(snap, g, it, scenario=scenario, floor_factor=3.0 if it == 1 else 5.0, **_bars(g, it))
         top = sorted(worst.items(), key=lambda kv: -kv[1][0] / kv[1][1])[:3]
         print(f"{what}: iteration {it}: worst " + ", ".join(f"{k} {e:.2e}/{t:.0e}" for k, (e, t) in top))
         assert not bad, f"{what}: after iteration {it}: {bad}"

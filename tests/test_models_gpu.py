@@ -1,16 +1,23 @@
-"""GPU parity tests of the generator / discriminator / R1 / PPL against the reference goldens and the oracle.
+"""GPU parity tests of the generator / discriminator / R1 / PPL against the reference goldens and the oracle, in the
+three precision modes of gif_b200.ops (measured table: profiles/r02_precision_report.jsonl, tools/precision_report.py):
 
-Network-level GRADIENTS are compared with the reference evaluated in float64 (``*_f64`` goldens): through ~14 leaky
-ReLUs the fp32 gradient is only piecewise continuous -- a pre-activation within rounding noise of zero flips its
-mask between two correct fp32 evaluation orders -- so the reference's own fp32 gradient differs from its fp64 value
-by ~1e-3 (L2) / 7e-3 (max) on D (tests/golden/ORACLE_VS_REFERENCE.txt).  The CUDA path in fp32 mode is therefore
-required to be within max(1e-3, 3x the reference's own fp32-vs-fp64 L2 error) of the fp64 truth in L2.  In tf32 mode
-(tensor-core convolutions) the forward activations carry ~3e-4 relative error, so ~3e-4 of all pre-activations flip their
-mask and the END-TO-END gradient deviates by ~1.7e-2 (L2) although every operator's backward is within 1e-3 on identical
-inputs (tests/test_ops_gpu.py, tests/test_conv_tc_gpu.py); the bar for those network-level tf32 gradients is 5e-2.
-Whole-network FORWARD outputs in tf32 mode accumulate the per-operator ~3e-4 over 7-14 convolutions (~sqrt(depth)):
-measured ~1e-3 on the 4-block generator; their bar is 3e-3, while every single operator is held to 1e-3
-(tests/test_ops_gpu.py, tests/test_conv_tc_gpu.py) and fp32 mode to 5e-5 / 1e-4.
+    quantity (vs reference golden)        fp32 SIMT    tf32 tcgen05    bf16x3 tcgen05      bar of BASELINE.json
+    G 32^2 / 256^2 forward (max-rel)      3.5e-6       0.9-1.2e-3      4.7e-5 / 8.8e-5     1e-3
+    D 64^2 / 256^2 scores                 1.4e-6       6.1e-4          3.9e-5 / 6.1e-5     1e-3
+    R1 penalty (double backward)          3.1e-5       1.3e-2          3.3e-4              1e-3
+    network gradients, L2 vs fp64         1.0-2.1e-3   2.0-3.2e-2      3.4-4.7e-3          (reference's own fp32: 0.95e-3)
+
+bf16x3 (the error-compensated contraction) is the mode that holds the 1e-3 bar end to end -- forward, scores and the R1
+penalty -- and it is the mode bench.py headlines; plain tf32 meets it per operator (tests/test_ops_tc_golden_gpu.py) but
+not through 7-14 chained layers, and is reported as the faster, lower-precision option.
+
+Network-level GRADIENTS are compared with the reference evaluated in float64 (``*_f64`` goldens).  Through ~14 leaky
+ReLUs the gradient is only piecewise continuous: a pre-activation within the forward error eps of zero flips its mask, so
+a forward error eps turns into an L2 gradient error ~sqrt(eps) whatever the arithmetic.  The reference's OWN fp32 gradient
+differs from its fp64 value by 0.95e-3 (L2, tests/golden/ORACLE_VS_REFERENCE.txt: eps ~1e-6); this repo's exact-fp32 path
+sits at 1.0-2.1e-3, bf16x3 (eps ~4e-5) at 3.4-4.7e-3, tf32 (eps ~1e-3) at 2-3e-2 -- the sqrt law, not an arithmetic
+defect (every operator's own backward is inside its forward bar on identical inputs, test_ops_tc_golden_gpu.py).  Bars:
+fp32 max(1e-3, 3x the reference's floor) resp. 5e-3 for G, bf16x3 8e-3, tf32 5e-2.
 """
 import math
 
@@ -56,7 +63,7 @@ D_PNAMES = ["convs.0.0.weight", "convs.1.conv1.0.weight", "convs.2.conv2.1.weigh
             "convs.2.conv2.2.bias", "final_conv.0.weight", "final_linear.0.weight", "final_linear.1.bias"]
 
 
-@pytest.mark.parametrize("mode,tol_fwd,tol_grad", [("fp32", 5e-5, 5e-3), ("tf32", 3e-3, 5e-2)])
+@pytest.mark.parametrize("mode,tol_fwd,tol_grad", [("fp32", 5e-5, 5e-3), ("tf32", 3e-3, 5e-2), ("bf16x3", 2e-4, 8e-3)])
 def test_generator_step3_golden(cuda, mode, tol_fwd, tol_grad):
     from gif_b200 import ops
     ops.set_precision(mode)
@@ -83,7 +90,7 @@ def test_generator_step3_golden(cuda, mode, tol_fwd, tol_grad):
         ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16x3", 3e-4)])
 def test_generator_256_golden(cuda, mode, tol):
     """BASELINE configs[1] shape (256^2, step 6), B=2: sampled reference output."""
     from gif_b200 import ops
@@ -101,7 +108,7 @@ def test_generator_256_golden(cuda, mode, tol):
         ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode,tol_fwd", [("fp32", 5e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol_fwd", [("fp32", 5e-5), ("tf32", 3e-3), ("bf16x3", 2e-4)])
 def test_discriminator_64_r1_golden(cuda, mode, tol_fwd):
     """Discriminator(64, 9ch) B=8: scores, R1 penalty (double backward), all gradients of softplus + R1."""
     from gif_b200 import losses, ops
@@ -115,12 +122,13 @@ def test_discriminator_64_r1_golden(cuda, mode, tol_fwd):
         assert tuple(scores.shape) == (8, 1)
         pen = losses.grad_penalty_loss([img], scores, step=None)
         assert gu.rel_err(scores.detach().cpu().numpy(), g["d64_scores"]) < tol_fwd
-        assert gu.rel_err(pen.detach().cpu().numpy(), g["d64_r1"]) < max(5 * tol_fwd, 5e-4)
+        # R1 penalty: 1e-3 (BASELINE.json's bar) in the exact and the compensated mode; plain tf32 cannot hold it (1.3e-2)
+        assert gu.rel_err(pen.detach().cpu().numpy(), g["d64_r1"]) < {"fp32": 5e-4, "bf16x3": 1e-3, "tf32": 3e-2}[mode]
         loss = F.softplus(-scores).mean() + pen.mean()
         named = dict(D.named_parameters())
         grads = torch.autograd.grad(loss, [img, cond] + [named[n] for n in D_PNAMES])
         floor = float(g["d64_gimg_ref32_l2err"])          # the reference's own fp32-vs-fp64 error
-        tol = max(1e-3, 3 * floor) if mode == "fp32" else 5e-2
+        tol = {"fp32": max(1e-3, 3 * floor), "bf16x3": 8e-3, "tf32": 5e-2}[mode]
         assert l2rel(grads[0].cpu().numpy(), g["d64_gimg_f64"]) < tol, "grad img"
         assert l2rel(grads[1].cpu().numpy(), g["d64_gcond_f64"]) < tol, "grad cond"
         for n, gr in zip(D_PNAMES, grads[2:]):
@@ -130,7 +138,7 @@ def test_discriminator_64_r1_golden(cuda, mode, tol_fwd):
         ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16x3", 3e-4)])
 def test_discriminator_256_golden(cuda, mode, tol):
     from gif_b200 import ops
     ops.set_precision(mode)

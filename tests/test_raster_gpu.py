@@ -177,10 +177,11 @@ def test_pytorch3d_convention_bit_exact(cuda, seed, S, size):
     fv = ndc_soup(2, 500, seed, size)
     zb, tri, bary = R.rasterize(torch.from_numpy(fv).to(cuda), S, S, convention="pytorch3d")
     zo, to, bo = RO.oracle_rasterize_pytorch3d(fv, S, S)
-    assert np.array_equal(tri.cpu().numpy(), to)
-    assert np.array_equal(zb.cpu().numpy(), zo)
-    assert np.array_equal(bary.cpu().numpy(), bo)
-    assert 0.05 < (to >= 0).mean() < 0.99
+    nt = int((tri.cpu().numpy() != to).sum())
+    assert nt == 0, f"pix_to_face differs at {nt} pixels (coverage {(to >= 0).mean():.3f})"
+    assert np.array_equal(zb.cpu().numpy(), zo), "zbuf differs"
+    assert np.array_equal(bary.cpu().numpy(), bo), "barycentrics differ"
+    assert (to >= 0).mean() > 0.05
     p2f, zbuf, b5, dists = R.rasterize_meshes(torch.from_numpy(fv).to(cuda), S)      # pytorch3d's return layout
     assert tuple(p2f.shape) == (2, S, S, 1) and p2f.dtype == torch.int64 and tuple(b5.shape) == (2, S, S, 1, 3) and dists is None
     assert int(p2f[1].max()) >= 500 and np.array_equal((p2f[..., 0] >= 0).cpu().numpy(), to >= 0)   # packed face offset b*F
