@@ -56,6 +56,34 @@ def test_render_matches_oracle(cuda, convention):
     assert 0.3 < float((t >= 0).mean()) < 0.9
 
 
+def test_render_matches_reference_renderer_golden(cuda):
+    """The CUDA conditioning render (pytorch3d convention) against the output of the UNMODIFIED reference Renderer.forward /
+    render_normal (tests/golden/render_composite.npz, oracle/make_render_golden.py: the reference's own code on top of the
+    pytorch3d-convention rasterisation oracle): textured image, normal image, alpha, quantised maps."""
+    import numpy as np
+    from gif_b200.flame_synth import flame_topology, flame_uv
+    from gif_b200.render import FlameRenderer
+    g = gu.load_golden("render_composite.npz")
+    _, faces = flame_topology()
+    uv, uvf = flame_uv()
+    S = g["images"].shape[-1]
+    R = FlameRenderer(faces, uv, uvf, image_size=S, convention="pytorch3d").to(cuda)
+    t = lambda k: torch.from_numpy(g[k]).to(cuda)
+    trans = RD.batch_orth_proj(torch.from_numpy(g["verts"]), torch.from_numpy(g["cam"]))
+    trans[:, :, 1:] = -trans[:, :, 1:]
+    out = R(t("verts"), trans.to(cuda), t("albedo"), t("lights"))        # host-projected vertices: identical rasteriser input
+    alpha = out["alpha"].cpu().numpy()
+    same = alpha == g["alpha"]
+    assert same.mean() > 0.9995                                           # ownership is bit-exact vs the oracle (test_raster_gpu)
+    m = torch.from_numpy(same).expand(-1, 3, -1, -1).numpy()
+    assert gu.rel_err(out["images"].cpu().numpy()[m], g["images"][m]) < 1e-4
+    assert gu.rel_err(out["normal_images"].cpu().numpy()[m], g["normal_images"][m]) < 1e-4
+    cond = out["cond"].cpu().numpy()
+    want = np.concatenate([np.clip(g["tex_quantised"], 0, 1) * 2 - 1, g["normal_quantised"] * 2 - 1], 1)
+    assert (np.abs(cond - want) > 2.0 / 255 + 1e-6).mean() < 1e-4        # at most one quantisation level, on isolated pixels
+    assert (np.abs(cond - want) > 1e-6).mean() < 5e-3
+
+
 def test_render_feeds_generator(cuda):
     """End to end: random FLAME-shaped params -> condition map -> generator image (the north-star data path)."""
     from gif_b200.flame_synth import flame_topology, flame_uv, synthetic_flame_params
