@@ -401,14 +401,14 @@ size_t conv2d_tc_workspace_bytes(int, int, int, int Ci, int, int, int Co, int k,
 
 int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
               int mode, int flip, int transposed, const ConvEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st,
-              bool x3) {
+              bool x3, bool prestaged) {
     GIFB200_REQUIRE(conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode), GIFB200_E_SHAPE, "conv2d_tc: unsupported shape");
     GIFB200_REQUIRE(ws && ws_bytes >= conv2d_tc_workspace_bytes(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode, transposed),
                     GIFB200_E_WORKSPACE, "conv2d_tc: workspace too small (see gifb200_conv2d_workspace_bytes)");
     GIFB200_REQUIRE(aligned16(x) && aligned16(y), GIFB200_E_ALIGN, "conv2d_tc: x / y must be 16-byte aligned");
     const int T = k * k;
     float* wst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
-    {
+    if (!prestaged) {     // prestaged: the caller kept the workspace of an earlier call with the same (w, flip, transposed, impl)
         const long long total = static_cast<long long>(T) * Co * Ci;
         int blocks = cdiv(total, 256 * 4);
         if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;

@@ -141,7 +141,9 @@ def _conv_raw(x, w, k, mode, flip, transposed, out_hw, epilogue=None, planes=Non
             impl = 1                         # shape outside the tensor-core path: exact fp32 SIMT
     elif nws > 0 and not _is_tf32(x):        # tensor-core path: operands must be tf32-representable (see gifb200.h)
         x = xin = _tag(_round_tf32_raw(x), True)
-    ws = _workspace(nws, x.device)
+    ws, staged = _staged_workspace(w, nws, flip, transposed, impl, (Ci, Co, k), x.device)
+    if staged:
+        impl |= 0x10                             # GIFB200_CONV_PRESTAGED: skip the staging pass
     prof = PROFILE is not None and nws > 0
     if prof:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -226,6 +228,7 @@ class _Conv(torch.autograd.Function):
         ctx.cfg = (k, mode, flip, transposed, tuple(x.shape[1:3]), _is_tf32(x_used))
         c = getattr(x_used, "_gifb200_planes", None)
         ctx.planes = c[1] if c is not None and c[0] == x_used._version else None   # bf16x3: wgrad reuses the split
+        ctx.wprep = getattr(w, "_gifb200_prep", None)
         return y
 
     @staticmethod
@@ -234,6 +237,8 @@ class _Conv(torch.autograd.Function):
         k, mode, flip, transposed, in_hw, x_tf32 = ctx.cfg
         _tag(x, x_tf32)
         _carry_planes(x, ctx.planes)
+        if ctx.wprep is not None:
+            w._gifb200_prep = ctx.wprep              # the input-gradient convolution reuses the staged-weight cache
         gx = gw = None
         if ctx.needs_input_grad[0]:
             # adj(S1, f, t) = (S1, !f, !t); adj(S2, f, t) = (T2, f, !t); adj(T2, f, t) = (S2, f, !t)
@@ -280,6 +285,7 @@ class _ConvBiasAct(torch.autograd.Function):
         ctx.cfg = (k, mode, slope, gain, tuple(x.shape[1:3]), _is_tf32(x_used), None if bias is None else bias.shape)
         c = getattr(x_used, "_gifb200_planes", None)
         ctx.planes = c[1] if c is not None and c[0] == x_used._version else None
+        ctx.wprep = getattr(w, "_gifb200_prep", None)
         return y
 
     @staticmethod
@@ -288,6 +294,8 @@ class _ConvBiasAct(torch.autograd.Function):
         k, mode, slope, gain, in_hw, x_tf32, bias_shape = ctx.cfg
         _tag(x, x_tf32)
         _carry_planes(x, ctx.planes)
+        if ctx.wprep is not None:
+            w._gifb200_prep = ctx.wprep
         gb = None
         if not torch.is_grad_enabled():
             # first-order backward: activation backward and bias gradient in one pass over (gy, y)
@@ -335,10 +343,64 @@ def conv2d(x, w, k, mode=S1, flip=False, transposed=False):
     return _Conv.apply(x, w, k, mode, flip, transposed, (conv_out_size(hi, k, mode), conv_out_size(wi, k, mode)))
 
 
+_prep_cache = {}     # (param data_ptr, shape, scale) -> (param version, tap-major tensor)
+_stage_cache = {}    # (prep key, flip, transposed, impl, conv shape) -> [weight version, persistent workspace]
+
+
+class _PrepWeight(torch.autograd.Function):
+    """(Co,Ci,k,k) parameter -> tap-major (k*k, Co, Ci) * scale, computed ONCE per parameter version: a network's weights
+    change once per optimiser step but every layer is evaluated 3-5 times per step (D: three forwards), so the permute +
+    scale (and, downstream, the staging of the tensor-core B operand, ``_stage_cache``) are shared by those calls.
+    The result lives in ONE persistent buffer per parameter, rewritten in place when the parameter's version changes: a
+    captured CUDA graph therefore always reads the buffer the (captured) recomputation of the current step wrote, whatever
+    the hit / miss pattern was at capture time.  An autograd graph that still holds the old contents when the buffer is
+    rewritten fails loudly (torch's version check), it cannot silently read new weights."""
+
+    @staticmethod
+    def forward(ctx, weight, scale):
+        co, ci, kh, kw = weight.shape
+        ctx.cfg = (co, ci, kh, kw, scale)
+        key = (weight.data_ptr(), (co, ci, kh, kw), float(scale))
+        hit = _prep_cache.get(key)
+        if hit is None or hit[0] != weight._version:
+            buf = hit[1] if hit is not None else torch.empty((kh * kw, co, ci), dtype=torch.float32, device=weight.device)
+            torch.mul(weight.detach().permute(2, 3, 0, 1), scale, out=buf.view(kh, kw, co, ci))    # one kernel, in place
+            hit = (weight._version, buf)
+            _prep_cache[key] = hit
+        alias = hit[1].detach()                 # a new tensor object on the cached storage: each call gets its own grad_fn
+        alias._gifb200_prep = (key, hit[0])
+        return alias
+
+    @staticmethod
+    def backward(ctx, g):
+        co, ci, kh, kw, scale = ctx.cfg
+        return (g.reshape(kh, kw, co, ci) * scale).permute(2, 3, 0, 1), None
+
+
 def prep_weight(weight, scale=1.0):
-    """(Co,Ci,k,k) parameter -> tap-major (k*k, Co, Ci) * scale.  Tiny tensors: plain (differentiable) torch glue."""
+    """(Co,Ci,k,k) parameter -> tap-major (k*k, Co, Ci) * scale (differentiable; cached per parameter version)."""
+    if weight.is_cuda and weight.dtype == torch.float32:
+        out = _PrepWeight.apply(weight, float(scale))
+        return out
     co, ci, kh, kw = weight.shape
     return (weight * scale).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
+
+
+def _staged_workspace(w, nws, flip, transposed, impl, shape_key, device):
+    """The persistent workspace holding the staged B operand of a cached prepared weight, and whether it is current
+    (GIFB200_CONV_PRESTAGED).  Weights that do not come out of ``prep_weight``'s cache use the shared scratch workspace."""
+    tag = getattr(w, "_gifb200_prep", None)
+    if tag is None or nws == 0:
+        return _workspace(nws, device), False
+    pkey, version = tag
+    key = (pkey, bool(flip), bool(transposed), impl, shape_key)
+    ent = _stage_cache.get(key)
+    if ent is None or ent[1].numel() < nws:
+        ent = [None, torch.empty(nws, dtype=torch.uint8, device=device)]
+        _stage_cache[key] = ent
+    fresh = ent[0] == version
+    ent[0] = version
+    return ent[1], fresh
 
 
 # --------------------------------------------------------------------------------------------- upfirdn2d
@@ -577,6 +639,7 @@ class _ModConvX3(torch.autograd.Function):
         y, _ = _conv_raw(x, w, k, mode, False, False, out_hw, planes=pl)
         ctx.save_for_backward(x, s, w)
         ctx.planes = pl
+        ctx.wprep = getattr(w, "_gifb200_prep", None)
         ctx.cfg = (k, mode, tuple(x.shape[1:3]))
         return y
 
@@ -584,6 +647,8 @@ class _ModConvX3(torch.autograd.Function):
     def backward(ctx, gy):
         x, s, w = ctx.saved_tensors
         k, mode, in_hw = ctx.cfg
+        if ctx.wprep is not None:
+            w._gifb200_prep = ctx.wprep
         adj = (gy, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
         if torch.is_grad_enabled():
             xs = chan_scale(x, s)

@@ -67,7 +67,13 @@ long long gifb200_launch_count(void);
  * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL).
  * Fused epilogue (ConvLayer = EqualConv2d -> FusedLeakyReLU, cl.py:752-799; nn.Conv2d + ReLU of NoiseInjection):
  *     y = lrelu(acc + bias[o], slope) * gain, optionally rounded to tf32;  act == 0 writes the plain accumulator
- *     (bias / slope / gain / round_tf32 ignored). */
+ *     (bias / slope / gain / round_tf32 ignored).
+ *
+ * GIFB200_CONV_PRESTAGED (OR-ed into impl, tensor-core paths only): the workspace still holds what an earlier call with the
+ * SAME (w contents, flip, transposed, impl) left there -- the staged B operand -- so the staging pass is skipped.  Weights
+ * change once per optimiser step but are used by 3-5 convolutions per step (D runs three forwards and two backwards): the
+ * caller keeps one workspace per (weight, variant) and sets the flag while the weight is unchanged. */
+#define GIFB200_CONV_PRESTAGED 0x10
 size_t gifb200_conv2d_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode,
                                       int transposed, int impl);
 int gifb200_conv2d(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co,

@@ -113,7 +113,7 @@ def compare(snap, golden, it, tol_d, tol_g, tol_moment, floor_factor=3.0, scenar
         ref64 = golden[f"f64|{scenario}it{it}|{key}"]
         floor = float(np.linalg.norm(ref - ref64) / max(np.linalg.norm(ref64), 1e-300))
         tag = key.split("|")[0]
-        base = tol_moment if key.endswith("exp_avg_sq") else (tol_d if tag == "d" else tol_g)
+        base = (tol_moment or 0.0) if key.endswith("exp_avg_sq") else (tol_d if tag == "d" else tol_g)
         err = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
         worst[key] = (err, max(base, floor_factor * floor))
     bad = {k: v for k, v in worst.items() if not v[0] < v[1]}
