@@ -10,6 +10,8 @@ Conventions
   * there is no CPU / eager fallback: non-CUDA tensors raise.
 """
 import math
+import os
+import weakref
 
 import torch
 
@@ -343,8 +345,10 @@ def conv2d(x, w, k, mode=S1, flip=False, transposed=False):
     return _Conv.apply(x, w, k, mode, flip, transposed, (conv_out_size(hi, k, mode), conv_out_size(wi, k, mode)))
 
 
-_prep_cache = {}     # (param data_ptr, shape, scale) -> (param version, tap-major tensor)
-_stage_cache = {}    # (prep key, flip, transposed, impl, conv shape) -> [weight version, persistent workspace]
+_NO_WEIGHT_CACHE = bool(os.environ.get("GIFB200_NO_WEIGHT_CACHE"))    # A/B switch: recompute the tap-major weights on every call
+_prep_cache = {}     # (id of the parameter, view offset, shape, scale) -> (weakref to the parameter, its version, buffer, serial)
+_stage_cache = {}    # (prep key, flip, transposed, impl, conv shape) -> [prep serial it was staged from, persistent workspace]
+_prep_serial = [0]   # bumped on every recomputation: what the staged-operand cache compares (immune to address / id reuse)
 
 
 class _PrepWeight(torch.autograd.Function):
@@ -360,15 +364,25 @@ class _PrepWeight(torch.autograd.Function):
     def forward(ctx, weight, scale):
         co, ci, kh, kw = weight.shape
         ctx.cfg = (co, ci, kh, kw, scale)
-        key = (weight.data_ptr(), (co, ci, kh, kw), float(scale))
+        base = weight._base if weight._base is not None else weight          # ``self.weight[0]`` is a view of the parameter
+        key = (id(base), weight.storage_offset(), (co, ci, kh, kw), float(scale))
         hit = _prep_cache.get(key)
-        if hit is None or hit[0] != weight._version:
-            buf = hit[1] if hit is not None else torch.empty((kh * kw, co, ci), dtype=torch.float32, device=weight.device)
+        # identity is checked through a weak reference: ids and addresses are reused once a network is freed, and a new
+        # parameter that lands on an old one's id with an equal version counter must not see its prepared weights
+        if hit is None or hit[0]() is not base or hit[1] != weight._version:
+            same = hit is not None and hit[0]() is base
+            buf = hit[2] if same else torch.empty((kh * kw, co, ci), dtype=torch.float32, device=weight.device)
             torch.mul(weight.detach().permute(2, 3, 0, 1), scale, out=buf.view(kh, kw, co, ci))    # one kernel, in place
-            hit = (weight._version, buf)
+            _prep_serial[0] += 1
+            hit = (weakref.ref(base), weight._version, buf, _prep_serial[0])
             _prep_cache[key] = hit
-        alias = hit[1].detach()                 # a new tensor object on the cached storage: each call gets its own grad_fn
-        alias._gifb200_prep = (key, hit[0])
+            if len(_prep_cache) > 4096:                                        # entries of freed networks
+                for k_ in [k_ for k_, v_ in _prep_cache.items() if v_[0]() is None]:
+                    del _prep_cache[k_]
+                    for sk in [sk for sk in _stage_cache if sk[0] == k_]:
+                        del _stage_cache[sk]
+        alias = hit[2].detach()                 # a new tensor object on the cached storage: each call gets its own grad_fn
+        alias._gifb200_prep = (key, hit[3])
         return alias
 
     @staticmethod
@@ -379,9 +393,8 @@ class _PrepWeight(torch.autograd.Function):
 
 def prep_weight(weight, scale=1.0):
     """(Co,Ci,k,k) parameter -> tap-major (k*k, Co, Ci) * scale (differentiable; cached per parameter version)."""
-    if weight.is_cuda and weight.dtype == torch.float32:
-        out = _PrepWeight.apply(weight, float(scale))
-        return out
+    if weight.is_cuda and weight.dtype == torch.float32 and not _NO_WEIGHT_CACHE:
+        return _PrepWeight.apply(weight, float(scale))
     co, ci, kh, kw = weight.shape
     return (weight * scale).permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous()
 
@@ -392,14 +405,14 @@ def _staged_workspace(w, nws, flip, transposed, impl, shape_key, device):
     tag = getattr(w, "_gifb200_prep", None)
     if tag is None or nws == 0:
         return _workspace(nws, device), False
-    pkey, version = tag
+    pkey, serial = tag
     key = (pkey, bool(flip), bool(transposed), impl, shape_key)
     ent = _stage_cache.get(key)
     if ent is None or ent[1].numel() < nws:
         ent = [None, torch.empty(nws, dtype=torch.uint8, device=device)]
         _stage_cache[key] = ent
-    fresh = ent[0] == version
-    ent[0] = version
+    fresh = ent[0] == serial
+    ent[0] = serial
     return ent[1], fresh
 
 
