@@ -82,6 +82,7 @@ def parse():
                          "the other mode is measured as an extra")
     ap.add_argument("--no-other-precision", action="store_true", help="skip the extra measurement in the other precision mode")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] / configs[3] side measurements")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own modules on this GPU (extra)")
     return ap.parse_args()
 
 
@@ -221,6 +222,40 @@ def cpu_arm_reference(batch, warm_up, vocab=1000):
                       + (f"warm-up {durs[0]:.1f} s, " if warm_up else "") +
                       f"R1 iteration {r1:.1f} s, plain {plain:.1f} s) combined as (15 plain + 1 R1) / 16; no path-length term "
                       f"(the reference's own is unrunnable, SURVEY 8 L2)"}
+
+
+def reference_on_gpu(batch=8, vocab=1000):
+    """EXTRA, not the baseline of the contract: the reference's own modules and unmodified train() on THIS GPU through stock
+    PyTorch / cuDNN (what a user of the reference gets on a B200 today), 1 warm-up + 2 timed plain iterations at a reduced
+    batch (its per-sample weight tensors and unfused upfirdn2d make batch 32 slow to autotune).  torch's stock precision flags (cuDNN convolutions may use TF32, matmuls fp32)."""
+    from oracle import ref_import, ref_train_runner
+    if not ref_import.available() or not torch.cuda.is_available():
+        return None
+    import contextlib
+    import warnings
+    ref = ref_import.load()
+    train = ref_import.load_train(with_gif_b200=False)
+    kw = dict(embedding_vocab_size=vocab, rendered_flame_ascondition=True, normal_maps_as_cond=True, core_tensor_res=4, n_mlp=8)
+    with contextlib.redirect_stdout(None):
+        G, Gr = ref.gen.StyledGenerator(**kw), ref.gen.StyledGenerator(**kw)
+        D = ref.disc.Discriminator(size=RES, num_color_chnls=9, channel_multiplier=2)
+    gen = torch.Generator().manual_seed(98)
+    batches = [(torch.rand(batch, 3, RES, RES, generator=gen) * 2 - 1, torch.rand(batch, 6, RES, RES, generator=gen) * 2 - 1,
+                torch.randn(batch, 159, generator=gen), torch.randint(0, vocab, (batch,), generator=gen)) for _ in range(3)]
+    stamps = []
+
+    def sync(*_a):
+        torch.cuda.synchronize()
+        stamps.append(time.perf_counter())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_train_runner.run(train, G, D, Gr, batches, RES, vocab, first_i=0, on_iteration_done=sync)
+    per_iter = (stamps[2] - stamps[0]) / 2
+    del G, D, Gr
+    torch.cuda.empty_cache()
+    return {"value": batch / per_iter, "unit": "images/sec", "batch": batch, "s_per_iteration": per_iter,
+            "note": "the reference's unmodified train() over its own modules on this GPU (stock PyTorch ops / cuDNN, torch's default "
+                    "precision flags: TF32 allowed in cuDNN convolutions), no R1 iteration in the sample; extra context, the contract's baseline is cpu_baseline"}
 
 
 def cpu_baseline(batch, warm_up, port_budget_s):
@@ -576,6 +611,14 @@ def main():
                 "executed_mma_tflops": ach * (3 if args.precision == "bf16x3" else 1),
                 "launches": len(prof), "kernel_ms_per_step": tot_ms / prof_steps,
                 "share_of_step": (tot_ms / prof_steps) / (ms / args.steps), "measured": prof_note}
+    ref_gpu = None
+    if not args.no_gpu_reference and world == 1:
+        try:
+            trainer._graphs = None
+            torch.cuda.empty_cache()
+            ref_gpu = reference_on_gpu()
+        except Exception as e:
+            ref_gpu = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     cb = None
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N=1 measurement
         cb = cpu_baseline(1, False, port_budget_s=40.0)   # the reference's own train() at batch 1: an R1 and a plain iteration
@@ -592,7 +635,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cb,
             "same_step_without_path_length_reg": extra_no_ppl,
             ("tf32_mode" if args.precision == "bf16x3" else "bf16x3_mode"): other_mode,
-            "other_configs": extras,
+            "other_configs": extras, "reference_modules_on_this_gpu": ref_gpu,
             "same_step_with_texture_interpolation_loss_instead_of_ppl": extra_tex}
     emit(line)
     if world > 1:

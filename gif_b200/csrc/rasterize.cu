@@ -37,6 +37,7 @@ namespace gifb200 {
 
 constexpr int TILE = 16;
 constexpr int kNoFace = 0x7fffffff;
+constexpr int kBwdLanes = 8;          // lanes per triangle in the backward gather
 constexpr float kP3dEps = 1e-8f;
 
 struct RasterGeom {
@@ -402,10 +403,16 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
                                                               const float* __restrict__ g_img2, const float* __restrict__ g_depth,
                                                               float* __restrict__ g_fv, float* __restrict__ g_col,
                                                               float* __restrict__ g_col2, int B, int F, int h, int w) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<long long>(B) * F) return;
-    const int b = static_cast<int>(i / F), f = static_cast<int>(i - static_cast<long long>(b) * F);
-    const long long fo = i * 9;
+    // kBwdLanes consecutive lanes share one triangle and interleave its bbox pixels: a warp's loop length is the LARGEST
+    // bbox among its triangles (each iteration is a dependent triangle-buffer read), so eight lanes per triangle cut the
+    // latency chain 8x; the moments are then summed over the lane group with shuffles (fixed order: still deterministic).
+    const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = gtid / kBwdLanes;
+    const int sub = static_cast<int>(gtid % kBwdLanes);
+    const bool live = i < static_cast<long long>(B) * F;
+    const long long ic = live ? i : 0;                  // dead lanes of the last warp shadow triangle 0 (no writes)
+    const int b = static_cast<int>(ic / F), f = static_cast<int>(ic - static_cast<long long>(b) * F);
+    const long long fo = ic * 9;
     const float* fc = fv + fo;
     const float x0 = fc[0], y0 = fc[1], z0 = fc[2], x1 = fc[3], y1 = fc[4], z1 = fc[5], x2 = fc[6], y2 = fc[7], z2 = fc[8];
     Moments M;
@@ -431,10 +438,13 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
         A = (x2 - x0) * (y1 - y0) - (y2 - y0) * (x1 - x0) + kP3dEps;
     }
     int xmin, xmax, ymin, ymax;
-    if (tri_bbox<CONV>(fc, w, h, xmin, xmax, ymin, ymax)) {
+    if (live && tri_bbox<CONV>(fc, w, h, xmin, xmax, ymin, ymax)) {
         const long long img = static_cast<long long>(b) * h * w;
-        for (int y = ymin; y <= ymax; ++y)
-            for (int x = xmin; x <= xmax; ++x) {
+        const int bw = xmax - xmin + 1, area = bw * (ymax - ymin + 1);
+        for (int pi = sub; pi < area; pi += kBwdLanes) {
+            {
+                const int ry = pi / bw;
+                const int y = ymin + ry, x = xmin + (pi - ry * bw);
                 const long long pix = img + static_cast<long long>(y) * w + x;
                 if (tri[pix] != f) continue;
                 float qx, qy;
@@ -472,7 +482,23 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
                     M.z[0] += gz; M.z[1] += gz * qx; M.z[2] += gz * qy;
                 }
             }
+        }
     }
+    // ---- sum the moments over the lane group (xor butterflies within aligned groups of kBwdLanes lanes)
+#pragma unroll
+    for (int o = 1; o < kBwdLanes; o <<= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            M.z[a] += __shfl_xor_sync(0xffffffffu, M.z[a], o);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                M.b[a][m] += __shfl_xor_sync(0xffffffffu, M.b[a][m], o);
+                M.c1[a][m] += __shfl_xor_sync(0xffffffffu, M.c1[a][m], o);
+                M.c2[a][m] += __shfl_xor_sync(0xffffffffu, M.c2[a][m], o);
+            }
+        }
+    }
+    if (!live || sub != 0) return;
     // ---- per-triangle algebra.  Gw[i][m]: moments of the total upstream gradient of barycentric i
     float Gw[3][3];
     const float* c = colors ? colors + fo : nullptr;
@@ -647,7 +673,7 @@ extern "C" int gifb200_rasterize_bwd_ex(const float* face_vertices, const float*
     GIFB200_REQUIRE(!g_img || face_colors, GIFB200_E_SHAPE, "rasterize_bwd: g_img needs face_colors");
     GIFB200_REQUIRE(!g_img2 || face_colors2, GIFB200_E_SHAPE, "rasterize_bwd: g_img2 needs face_colors2");
     if (B == 0 || F == 0) return GIFB200_OK;
-    const long long ntri = static_cast<long long>(B) * F;
+    const long long ntri = static_cast<long long>(B) * F * kBwdLanes;       // threads: kBwdLanes lanes per triangle
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (convention == 0)
         raster_bwd_face_kernel<0><<<cdiv(ntri, 128), 128, 0, st>>>(face_vertices, face_colors, face_colors2, triangle, g_bary, g_img,

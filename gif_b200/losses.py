@@ -23,9 +23,11 @@ def l2_reg(model):
 
 def grad_penalty_loss(inputs, outs, step):
     """losses.py:87-99: per-sample weight * ||d sum(outs) / d input||^2 (weight 5.0 when step is None)."""
+    from . import ops
     grad_penalty = 0
     for inp_idx, inpt in enumerate(inputs):
-        grad_real = grad(outputs=outs.sum(), inputs=inpt, create_graph=True)[0]
+        with ops.input_gradient_only():          # d scores / d image: no convolution weight gradients on the way
+            grad_real = grad(outputs=outs.sum(), inputs=inpt, create_graph=True)[0]
         if step is not None:
             w = 1 + step - inp_idx
             w = 0.05 / (w * np.log2(1 + w))
@@ -53,7 +55,9 @@ class PathLengthRegularizor:
         if pl_noise is None:
             pl_noise = torch.randn(fake.shape, device=fake.device)
         pl_noise = pl_noise / np.sqrt(np.prod(fake.shape))                       # losses.py:114
-        pl_grads = grad(outputs=torch.sum(fake * pl_noise), inputs=w, create_graph=True)[0]
+        from . import ops
+        with ops.input_gradient_only():          # d image / d w: the generator's weight gradients are not part of it
+            pl_grads = grad(outputs=torch.sum(fake * pl_noise), inputs=w, create_graph=True)[0]
         pl_lengths = torch.mean(torch.sqrt(torch.sum(torch.pow(pl_grads, 2), dim=1)))   # losses.py:116
         # losses.py:119 as written (no stop-gradient: the new mean == decay * length and carries its gradient into the
         # penalty); only the value kept for the next call is detached so that no graph outlives the iteration.

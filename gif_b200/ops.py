@@ -24,6 +24,25 @@ WGRAD_IMPL = 0                # same for the weight-gradient kernel
 _PRECISION = "tf32"
 
 
+_WEIGHT_GRADS = [True]
+
+
+class input_gradient_only:
+    """``with ops.input_gradient_only():`` around a ``torch.autograd.grad(..., inputs=<activations / latents>)`` call: a custom
+    Function's ``ctx.needs_input_grad`` says which inputs REQUIRE grad, not which gradients this particular call asks for, so
+    the R1 penalty (gradient w.r.t. the image) and the path-length term (gradient w.r.t. w) would compute -- and autograd would
+    throw away -- the weight gradient of every convolution on the way: a third of the tensor work of that pass.  Inside the
+    block the convolution Functions skip their weight gradients."""
+
+    def __enter__(self):
+        self.prev = _WEIGHT_GRADS[0]
+        _WEIGHT_GRADS[0] = False
+
+    def __exit__(self, *a):
+        _WEIGHT_GRADS[0] = self.prev
+        return False
+
+
 def set_precision(mode):
     """"tf32":   convolutions that qualify run on tcgen05 (kind::tf32, fp32 accumulate) and their operand producers round
                  to tf32 (~3e-4 per operator);
@@ -245,7 +264,7 @@ class _Conv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # adj(S1, f, t) = (S1, !f, !t); adj(S2, f, t) = (T2, f, !t); adj(T2, f, t) = (S2, f, !t)
             gx = _Conv.apply(gy, w, k, _ADJ_MODE[mode], (not flip) if mode == S1 else flip, not transposed, in_hw)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _WEIGHT_GRADS[0]:
             gw = _ConvWgrad.apply(x, gy, k, mode, flip, transposed)
         return gx, gw, None, None, None, None, None
 
@@ -327,7 +346,7 @@ class _ConvBiasAct(torch.autograd.Function):
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = _Conv.apply(gt, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _WEIGHT_GRADS[0]:
             gw = _ConvWgrad.apply(x, gt, k, mode, False, False)
         return gx, gw, gb, None, None, None, None, None, None
 
@@ -664,11 +683,12 @@ class _ModConvX3(torch.autograd.Function):
             w._gifb200_prep = ctx.wprep
         adj = (gy, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
         if torch.is_grad_enabled():
-            xs = chan_scale(x, s)
             gxs = _Conv.apply(*adj) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
             gx = chan_scale(gxs, s) if ctx.needs_input_grad[0] else None
             gs = spatial_dot(gxs, x) if ctx.needs_input_grad[1] else None
-            gw = _ConvWgrad.apply(xs, gy, k, mode, False, False) if ctx.needs_input_grad[2] else None
+            gw = None
+            if ctx.needs_input_grad[2] and _WEIGHT_GRADS[0]:
+                gw = _ConvWgrad.apply(chan_scale(x, s), gy, k, mode, False, False)
             return gx, gs, gw, None, None, None
         gy = _c(gy)
         gx = gs = gw = None
@@ -679,7 +699,7 @@ class _ModConvX3(torch.autograd.Function):
             gx = torch.empty_like(gxs)
             gs = torch.empty((B, C), dtype=torch.float32, device=gy.device)
             check(lib.gifb200_scale_bwd(ptr(gxs), ptr(x), ptr(s), ptr(gx), ptr(gs), B, P, C, 0, stream()), "gifb200_scale_bwd")
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[2] and _WEIGHT_GRADS[0]:
             gw = _wgrad_raw(x, gy, k, mode, False, False, x_planes=ctx.planes)
         return gx, gs, gw, None, None, None
 

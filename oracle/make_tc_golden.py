@@ -103,6 +103,30 @@ def res_block(tag, ci, co, b, hw):
     print(tag, "fp32 floors:", [f"{OUT[k]:.1e}" for k in OUT if k.startswith(tag) and k.endswith("_floor")])
 
 
+def noise_injection(tag, cin, cout, b, hw):
+    """NoiseInjection (cl.py:388-431): image + Conv3x3(ReLU(Conv3x3(ReLU(Conv3x3(cond))))) -- where the FLAME condition
+    enters the generator; small-K convolutions (6 -> 12 -> 24 -> Co) that the tensor-core modes run zero-padded to 32."""
+    res = []
+    pn = ["noise_conv.0.weight", "noise_conv.0.bias", "noise_conv.2.weight", "noise_conv.4.weight", "noise_conv.4.bias"]
+    for dt in (torch.float64, torch.float32):
+        m = R.cl.NoiseInjection(cin, cout)
+        sd = m.state_dict()
+        g = torch.Generator().manual_seed(150)
+        for kk in sd:
+            sd[kk] = torch.randn(sd[kk].shape, generator=g) * (0.05 if "bias" in kk else 0.3)
+        m.load_state_dict(sd)
+        m = m.to(dt)
+        img = gu.randn((b, cout, hw, hw), 151).to(dt).requires_grad_(True)
+        cond = gu.rand_uniform((b, cin, hw, hw), 152).to(dt).requires_grad_(True)
+        y = m(img, cond)
+        gy = gu.randn(tuple(y.shape), 153).to(dt)
+        named = dict(m.named_parameters())
+        grads = torch.autograd.grad((y * gy).sum(), [img, cond] + [named[n] for n in pn])
+        res.append([y] + list(grads))
+    record(tag, ["y", "gimg", "gcond"] + ["g_" + n for n in pn], res[0], res[1])
+    print(tag, "fp32 floors:", [f"{OUT[k]:.1e}" for k in OUT if k.startswith(tag) and k.endswith("_floor")])
+
+
 def main():
     torch.manual_seed(0)
     modconv("mc_plain", 64, 64, 3, True, False, 3, 16)
@@ -114,6 +138,7 @@ def main():
     equal_conv("ec_s2", 64, 64, 3, 2, 0, 2, 33)
     equal_conv("ec_1x1", 64, 32, 1, 1, 0, 2, 32)
     res_block("rb", 64, 128, 2, 32)
+    noise_injection("ni", 6, 64, 2, 32)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ops_tc.npz"), **OUT)
     print("wrote tests/golden/ops_tc.npz:", len(OUT), "arrays,",
           os.path.getsize(os.path.join(ROOT, "tests", "golden", "ops_tc.npz")) // 1024, "KiB")

@@ -53,13 +53,17 @@ def cuda_calls_are_noops_without_a_gpu(force=False):
     if torch.cuda.is_available() and not force:
         yield
         return
-    t_cuda, m_cuda = torch.Tensor.cuda, torch.nn.Module.cuda
+    t_cuda, m_cuda, avail = torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.is_available
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self
+    # nn.DataParallel moves its module to cuda:0 with ``.to()`` when exactly one GPU is visible (and scatters the inputs
+    # there): with a GPU in the box the "CPU" arm silently ran on it through cuDNN.  No visible device type -> device_ids = []
+    # -> DataParallel.forward calls the module where it is.
+    torch.cuda.is_available = lambda: False
     try:
         yield
     finally:
-        torch.Tensor.cuda, torch.nn.Module.cuda = t_cuda, m_cuda
+        torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.is_available = t_cuda, m_cuda, avail
 
 
 def run(train_mod, G, D, Gr, batches, res, vocab, first_i=0, on_iteration_done=None, force_cpu=False, stamps=None):

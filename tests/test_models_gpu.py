@@ -90,7 +90,7 @@ def test_generator_step3_golden(cuda, mode, tol_fwd, tol_grad):
         ops.set_precision("tf32")
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16x3", 3e-4)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16x3", 5e-4)])
 def test_generator_256_golden(cuda, mode, tol):
     """BASELINE configs[1] shape (256^2, step 6), B=2: sampled reference output."""
     from gif_b200 import ops
@@ -154,9 +154,20 @@ def test_discriminator_256_golden(cuda, mode, tol):
         ops.set_precision("tf32")
 
 
-def test_path_length_regulariser_vs_oracle(cuda, fp32_mode):
+@pytest.mark.parametrize("mode,tol_val,tol_grad", [("fp32", 1e-3, 1e-2), ("bf16x3", 2e-3, 3e-2), ("tf32", 3e-2, 3e-1)])
+def test_path_length_regulariser_vs_oracle(cuda, mode, tol_val, tol_grad):
     """PPL (parity UNPINNED in the reference): the adopted rule, CUDA path vs oracle autograd, incl. the
-    gradient of the penalty w.r.t. a generator weight (needs the double backward of every G op)."""
+    gradient of the penalty w.r.t. a generator weight (needs the double backward of every G op) -- in all three precision
+    modes (the penalty is a second-order quantity: ||d img / d w|| through 5 modulated convolutions and their activations)."""
+    from gif_b200 import losses, ops
+    ops.set_precision(mode)
+    try:
+        _ppl_case(cuda, mode, tol_val, tol_grad)
+    finally:
+        ops.set_precision("tf32")
+
+
+def _ppl_case(cuda, mode, tol_val, tol_grad):
     from gif_b200 import losses
     G, sd = make_g(cuda)
     cond = gu.rand_uniform((2, 6, 16, 16), 60)
@@ -171,9 +182,12 @@ def test_path_length_regulariser_vs_oracle(cuda, fp32_mode):
     reg = losses.PathLengthRegularizor()
     pen = reg.path_length_reg(G, step=2, alpha=1, input_indices=idx.to(cuda), cond=cond.to(cuda), pl_noise=noise.to(cuda))
     (g_c,) = torch.autograd.grad(pen, dict(G.named_parameters())[pname])
-    assert abs(float(pen.detach()) - float(pen_o.detach())) / abs(float(pen_o.detach())) < 1e-3
-    assert abs(float(reg.pl_moving_mean) - float(ema_o)) / abs(float(ema_o)) < 1e-3
-    assert l2rel(g_c.cpu().numpy(), g_o.numpy()) < 1e-2      # mask-flip noise floor of a double backward, see module docstring
+    e_pen = abs(float(pen.detach()) - float(pen_o.detach())) / abs(float(pen_o.detach()))
+    e_ema = abs(float(reg.pl_moving_mean) - float(ema_o)) / abs(float(ema_o))
+    e_g = l2rel(g_c.cpu().numpy(), g_o.numpy())
+    print(f"PPL [{mode}]: penalty {e_pen:.2e}  ema {e_ema:.2e}  grad L2 {e_g:.2e}")
+    assert e_pen < tol_val and e_ema < tol_val
+    assert e_g < tol_grad      # mask-flip noise floor of a double backward, see module docstring
 
 
 def test_drop_in_module_names():

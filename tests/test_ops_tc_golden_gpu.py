@@ -141,3 +141,33 @@ def test_res_block_tc_shapes(cuda, gold, mode, tol):
         print(f"rb [{mode}]: " + "  ".join(rep))
     finally:
         ops.set_precision("tf32")
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_noise_injection_tc_shapes(cuda, gold, mode, tol):
+    """NoiseInjection (cl.py:388-431): where the 6-channel FLAME condition enters the generator.  Three chained
+    small-K convolutions with ReLUs (run zero-padded to 32 channels on the tensor cores): output and first derivatives
+    w.r.t. the image, the CONDITION and the convolution parameters (forward bar: 2x the operator bar, three contractions)."""
+    from gif_b200 import ops
+    from gif_b200.model import stylegan2_common_layers as cl
+    ops.set_precision(mode)
+    try:
+        m = cl.NoiseInjection(6, 64).to(cuda)
+        sd = m.state_dict()
+        gen = torch.Generator().manual_seed(150)
+        for kk in sd:
+            sd[kk] = torch.randn(sd[kk].shape, generator=gen) * (0.05 if "bias" in kk else 0.3)
+        m.load_state_dict(sd)
+        img = gu.randn((2, 64, 32, 32), 151).to(cuda).requires_grad_(True)
+        cond = gu.rand_uniform((2, 6, 32, 32), 152).to(cuda).requires_grad_(True)
+        y = m(img, cond)
+        gy = gu.randn(tuple(y.shape), 153).to(cuda)
+        named = dict(m.named_parameters())
+        pn = ["noise_conv.0.weight", "noise_conv.0.bias", "noise_conv.2.weight", "noise_conv.4.weight", "noise_conv.4.bias"]
+        grads = torch.autograd.grad((y * gy).sum(), [img, cond] + [named[n] for n in pn])
+        rep = []
+        _check("ni", ["y", "gimg", "gcond"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep,
+               grad_tol=5e-2 if mode == "tf32" else None)      # gradients through the two ReLUs: see test_res_block_tc_shapes
+        print(f"ni [{mode}]: " + "  ".join(rep))
+    finally:
+        ops.set_precision("tf32")

@@ -135,7 +135,9 @@ def test_two_attribute_sets_in_one_pass(cuda):
     gb = torch.autograd.grad((R.rasterize(fb, 128, 128, nb)[2] * g2).sum(), [fb, nb])
     assert torch.equal(grads[1], ga[1]) and torch.equal(grads[2], gb[1])
     ref = ga[0] + gb[0]
-    assert float((grads[0] - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # the vertex gradient is algebra on summed moments: (moments of set 1 + moments of set 2) vs two separately rounded
+    # results -- fp32 reassociation through ill-conditioned slivers (1 / den); same bar as the backward-vs-autograd tests
+    assert float((grads[0] - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
 
 
 def test_backward_is_deterministic_and_overwrites(cuda):
