@@ -38,6 +38,8 @@ SIGNATURES = {
     "gifb200_tail_bwd": (_i, [_p] * 8 + [_i, _i, _i, _f, _f, _i, _p]),
     "gifb200_tail_bwd_planes": (_i, [_p] * 8 + [_i, _i, _i, _f, _f, _p, _p, _p]),
     "gifb200_scale_bwd": (_i, [_p] * 5 + [_i, _i, _i, _i, _p]),
+    "gifb200_tail_bwd2": (_i, [_p] * 9 + [_i, _i, _i, _f, _f, _p, _p]),
+    "gifb200_adam_step": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _p]),
     "gifb200_spatial_dot": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "gifb200_axpby": (_i, [_p, _p, _p, _ll, _f, _f, _i, _p]),
     "gifb200_demod": (_i, [_p, _p, _p, _i, _i, _i, _f, _p]),

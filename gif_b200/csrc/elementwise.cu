@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) tail_bwd_kernel(const float* __restrict__
             sb += g;
             if (gd) sd += g * __ldcs(acc + i);
             if (rtf32) { g = round_tf32(g); ga = round_tf32(ga); }
-            gt[i] = g;
+            if (gt) gt[i] = g;
             if (gacc) gacc[i] = ga;
         }
     }
@@ -320,6 +320,104 @@ __global__ void __launch_bounds__(256) scale_bwd_vec_kernel(const float* __restr
 #pragma unroll
         for (int j = 0; j < TY; ++j) f4_add(t, sm[j][tx]);
         f4_atomic_add(gs + static_cast<long long>(b) * C + c, t);
+    }
+}
+
+
+// Second-order pass of the two kernels above (path-length regulariser: the derivative of a first-order backward that was
+// recorded with create_graph).  The first-order map is, with m = gain*(y>0 ? 1 : slope) (m = 1 when y is null: the
+// modulation variant), per (b, pixel, c):   gacc = gy*m*d[b,c]      gd[b,c] = sum_pixels gy*m*acc
+// and given the upstream pair (gg = dL/dgacc, ggd = dL/dgd) this writes, in ONE pass over (gg, gy, y, acc):
+//   ggy = m*(gg*d + ggd*acc)   (dL/dgy)      gx2 = gy*m*ggd   (dL/dacc)      gdd[b,c] += sum gg*gy*m   (dL/dd)
+// instead of the closed-set composition (act_bwd, chan_scale x3, spatial_dot, and autograd's gradient-sum adds).
+__global__ void __launch_bounds__(256) tail_bwd2_kernel(const float* __restrict__ gg, const float* __restrict__ ggd,
+                                                        const float* __restrict__ gy, const float* __restrict__ y,
+                                                        const float* __restrict__ acc, const float* __restrict__ d,
+                                                        float* __restrict__ ggy, float* __restrict__ gx2,
+                                                        float* __restrict__ gdd, int rows, int C, int rows_per_block,
+                                                        float slope, float gain) {
+    __shared__ float sm[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float sd = 0.f;
+    if (c < C) {
+        const float dv = d ? d[static_cast<long long>(b) * C + c] : 1.f;
+        const float qv = ggd ? ggd[static_cast<long long>(b) * C + c] : 0.f;
+        const long long base = (static_cast<long long>(b) * rows) * C + c;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const long long i = base + static_cast<long long>(r) * C;
+            const float m = y ? gain * (__ldcs(y + i) > 0.f ? 1.f : slope) : 1.f;
+            const float gm = __ldcs(gy + i) * m;
+            float u = 0.f;
+            if (gg) { const float G = __ldcs(gg + i); u = G * dv; sd += G * gm; }
+            if (ggd) { u += qv * __ldcs(acc + i); if (gx2) gx2[i] = gm * qv; }
+            if (ggy) ggy[i] = m * u;
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = sd;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C && gdd && gg) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        atomicAdd(gdd + static_cast<long long>(b) * C + c, t);
+    }
+}
+
+template <int TX>
+__global__ void __launch_bounds__(256) tail_bwd2_vec_kernel(const float* __restrict__ gg, const float* __restrict__ ggd,
+                                                            const float* __restrict__ gy, const float* __restrict__ y,
+                                                            const float* __restrict__ acc, const float* __restrict__ d,
+                                                            float* __restrict__ ggy, float* __restrict__ gx2,
+                                                            float* __restrict__ gdd, int rows, int C, int rows_per_block,
+                                                            float slope, float gain, __nv_bfloat16* __restrict__ ggy_planes,
+                                                            long long total) {
+    constexpr int TY = 256 / TX;
+    __shared__ float4 sm[TY][TX];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = (blockIdx.x * TX + tx) * 4;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    float4 sd = f4_zero();
+    const float4 dv = d ? *reinterpret_cast<const float4*>(d + static_cast<long long>(b) * C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 qv = ggd ? *reinterpret_cast<const float4*>(ggd + static_cast<long long>(b) * C + c) : f4_zero();
+    const long long base = (static_cast<long long>(b) * rows) * C + c;
+    const float neg = gain * slope;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += TY) {
+        const long long i = base + static_cast<long long>(r) * C;
+        const float4 g0 = __ldcs(reinterpret_cast<const float4*>(gy + i));
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (y) {
+            const float4 yv = __ldcs(reinterpret_cast<const float4*>(y + i));
+            m = make_float4(yv.x > 0.f ? gain : neg, yv.y > 0.f ? gain : neg, yv.z > 0.f ? gain : neg, yv.w > 0.f ? gain : neg);
+        }
+        const float4 gm = make_float4(g0.x * m.x, g0.y * m.y, g0.z * m.z, g0.w * m.w);
+        float4 u = f4_zero();
+        if (gg) {
+            const float4 G = __ldcs(reinterpret_cast<const float4*>(gg + i));
+            u = make_float4(G.x * dv.x, G.y * dv.y, G.z * dv.z, G.w * dv.w);
+            sd.x += G.x * gm.x; sd.y += G.y * gm.y; sd.z += G.z * gm.z; sd.w += G.w * gm.w;
+        }
+        if (ggd) {
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(acc + i));
+            u.x += qv.x * a.x; u.y += qv.y * a.y; u.z += qv.z * a.z; u.w += qv.w * a.w;
+            if (gx2) *reinterpret_cast<float4*>(gx2 + i) = make_float4(gm.x * qv.x, gm.y * qv.y, gm.z * qv.z, gm.w * qv.w);
+        }
+        const float4 o = make_float4(m.x * u.x, m.y * u.y, m.z * u.z, m.w * u.w);
+        if (ggy) *reinterpret_cast<float4*>(ggy + i) = o;
+        if (ggy_planes) store_planes4(ggy_planes, total, i, o);
+    }
+    sm[ty][tx] = sd;
+    __syncthreads();
+    if (ty == 0 && gdd && gg) {
+        float4 t = f4_zero();
+#pragma unroll
+        for (int j = 0; j < TY; ++j) f4_add(t, sm[j][tx]);
+        f4_atomic_add(gdd + static_cast<long long>(b) * C + c, t);
     }
 }
 
@@ -755,7 +853,7 @@ static int tail_bwd_impl(const float* gy, const float* y, const float* acc, cons
                          float* gb, float* gd, int B, int P, int C, float slope, float gain, int rtf32, void* gt_planes,
                          void* gacc_planes, gifb200_stream_t stream) {
     GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "tail_bwd: bad shape");
-    GIFB200_REQUIRE(gt || gt_planes, GIFB200_E_SHAPE, "tail_bwd: gt or gt_planes is required");
+    GIFB200_REQUIRE(gt || gt_planes || gacc, GIFB200_E_SHAPE, "tail_bwd: gt, gt_planes or gacc is required");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B == 0) return GIFB200_OK;
     if (gb) {
@@ -785,7 +883,7 @@ static int tail_bwd_impl(const float* gy, const float* y, const float* acc, cons
         GIFB200_LAUNCH_CHECK("tail_bwd_vec_kernel");
         return GIFB200_OK;
     }
-    GIFB200_REQUIRE(!planes && gt, GIFB200_E_ALIGN, "tail_bwd: the planes outputs need C % 32 == 0 and 16-byte aligned pointers");
+    GIFB200_REQUIRE(!planes, GIFB200_E_ALIGN, "tail_bwd: the planes outputs need C % 32 == 0 and 16-byte aligned pointers");
     const int cb = cdiv(C, 32);
     int rpb;
     const int rb = rows_split(P, cb, B, &rpb);
@@ -833,6 +931,46 @@ int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx
     GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "scale_bwd: grid too large");
     scale_bwd_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gy, x, s, gx, gs, P, C, rpb, rtf32);
     GIFB200_LAUNCH_CHECK("scale_bwd_kernel");
+    return GIFB200_OK;
+}
+
+int gifb200_tail_bwd2(const float* gg, const float* ggd, const float* gy, const float* y, const float* acc, const float* d,
+                      float* ggy, float* gx2, float* gdd, int B, int P, int C, float slope, float gain, void* ggy_planes,
+                      gifb200_stream_t stream) {
+    GIFB200_REQUIRE(B >= 0 && P >= 0 && C > 0, GIFB200_E_SHAPE, "tail_bwd2: bad shape");
+    GIFB200_REQUIRE(gy && (gg || ggd), GIFB200_E_SHAPE, "tail_bwd2: gy and at least one upstream gradient are required");
+    GIFB200_REQUIRE(!ggd || acc, GIFB200_E_SHAPE, "tail_bwd2: ggd needs acc");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) return GIFB200_OK;
+    if (gdd) {
+        cudaError_t e = cudaMemsetAsync(gdd, 0, sizeof(float) * static_cast<size_t>(B) * C, st);
+        if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "tail_bwd2 memset", cudaGetErrorString(e));
+    }
+    if (P == 0) return GIFB200_OK;
+    if (C % 32 == 0 && aligned16(gy) && (!gg || aligned16(gg)) && (!ggd || (aligned16(ggd) && aligned16(acc))) && (!y || aligned16(y)) &&
+        (!d || aligned16(d)) && (!ggy || aligned16(ggy)) && (!gx2 || aligned16(gx2)) && (!gdd || aligned16(gdd)) &&
+        (!ggy_planes || aligned16(ggy_planes))) {
+        const int tx = vec_lanes(C);
+        int rpb;
+        const int cbv = C / (4 * tx);
+        const int rb = rows_split_vec(P, cbv, B, 256 / tx, &rpb);
+        GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "tail_bwd2: grid too large");
+        const dim3 grid(cbv, rb, B);
+        __nv_bfloat16* pp = static_cast<__nv_bfloat16*>(ggy_planes);
+        const long long total = static_cast<long long>(B) * P * C;
+        if (tx == 32) tail_bwd2_vec_kernel<32><<<grid, 256, 0, st>>>(gg, ggd, gy, y, acc, d, ggy, gx2, gdd, P, C, rpb, slope, gain, pp, total);
+        else if (tx == 16) tail_bwd2_vec_kernel<16><<<grid, 256, 0, st>>>(gg, ggd, gy, y, acc, d, ggy, gx2, gdd, P, C, rpb, slope, gain, pp, total);
+        else tail_bwd2_vec_kernel<8><<<grid, 256, 0, st>>>(gg, ggd, gy, y, acc, d, ggy, gx2, gdd, P, C, rpb, slope, gain, pp, total);
+        GIFB200_LAUNCH_CHECK("tail_bwd2_vec_kernel");
+        return GIFB200_OK;
+    }
+    GIFB200_REQUIRE(!ggy_planes, GIFB200_E_ALIGN, "tail_bwd2: the planes output needs C % 32 == 0 and 16-byte aligned pointers");
+    const int cb = cdiv(C, 32);
+    int rpb;
+    const int rb = rows_split(P, cb, B, &rpb);
+    GIFB200_REQUIRE(B <= 65535 && rb <= 65535, GIFB200_E_SHAPE, "tail_bwd2: grid too large");
+    tail_bwd2_kernel<<<dim3(cb, rb, B), dim3(32, 8), 0, st>>>(gg, ggd, gy, y, acc, d, ggy, gx2, gdd, P, C, rpb, slope, gain);
+    GIFB200_LAUNCH_CHECK("tail_bwd2_kernel");
     return GIFB200_OK;
 }
 

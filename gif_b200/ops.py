@@ -32,7 +32,10 @@ class input_gradient_only:
     Function's ``ctx.needs_input_grad`` says which inputs REQUIRE grad, not which gradients this particular call asks for, so
     the R1 penalty (gradient w.r.t. the image) and the path-length term (gradient w.r.t. w) would compute -- and autograd would
     throw away -- the weight gradient of every convolution on the way: a third of the tensor work of that pass.  Inside the
-    block the convolution Functions skip their weight gradients."""
+    block the convolution Functions skip their weight gradients, the tails skip their bias and noise-branch gradients (side
+    branches that end in parameters or in the condition receive NO gradient: ask only for gradients w.r.t. the image / the
+    latent chain), and the StyledConv tail / modulation backwards are recorded as single nodes with a fused second-order
+    kernel (``_TailBwdCG``)."""
 
     def __enter__(self):
         self.prev = _WEIGHT_GRADS[0]
@@ -341,7 +344,7 @@ class _ConvBiasAct(torch.autograd.Function):
                 gb = gbf.reshape(bias_shape)
         else:
             gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())
-            if bias_shape is not None and ctx.needs_input_grad[2]:
+            if bias_shape is not None and ctx.needs_input_grad[2] and _WEIGHT_GRADS[0]:
                 gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
         gx = gw = None
         if ctx.needs_input_grad[0]:
@@ -529,6 +532,11 @@ class _BiasAct(torch.autograd.Function):
             gx = (gacc if rowscale is not None else gt) if ctx.needs_input_grad[0] else None
             return (gx, gd, gt if (has_add and ctx.needs_input_grad[2]) else None,
                     gb.reshape(bias_shape) if want_b else None, None, None, None)
+        if not _WEIGHT_GRADS[0] and rowscale is not None:
+            # input_gradient_only (path-length pass): one node, fused second-order rule; no noise-branch / bias gradients
+            gx, grs = _TailBwdCG.apply(gy, y, x, rowscale, slope, gain, True)
+            return (gx if ctx.needs_input_grad[0] else None, grs if ctx.needs_input_grad[1] else None, None, None, None, None,
+                    None)
         gt = act_bwd(gy, y, slope, gain, rt=tf32_enabled())   # gradient w.r.t. the pre-activation t (feeds dgrad/wgrad)
         gx = grs = gadd = gb = None
         if ctx.needs_input_grad[0]:
@@ -537,9 +545,68 @@ class _BiasAct(torch.autograd.Function):
             grs = spatial_dot(gt, x)
         if has_add and ctx.needs_input_grad[2]:
             gadd = gt
-        if bias_shape is not None and ctx.needs_input_grad[3]:
+        if bias_shape is not None and ctx.needs_input_grad[3] and _WEIGHT_GRADS[0]:
             gb = rows_sum(gt.reshape(1, -1, gt.shape[-1])).reshape(bias_shape)
         return gx, grs, gadd, gb, None, None, None
+
+
+class _TailBwdCG(torch.autograd.Function):
+    """The first-order backward of the StyledConv tail (y given: gacc = gy*m(y)*d, gd = sum_p gy*m(y)*acc) or of the input
+    modulation (y None: m = 1) as ONE differentiable node with a fused second-order pass (gifb200_tail_bwd2), for the
+    create_graph pass of the path-length regulariser -- instead of act_bwd + chan_scale + spatial_dot, whose recorded graph
+    costs five more elementwise kernels and autograd's gradient-sum adds per layer in the double backward.  Only taken inside
+    ``input_gradient_only()`` (the noise-branch and bias gradients are not produced).  Second order is the last: its
+    backward is not differentiable again."""
+
+    @staticmethod
+    def forward(ctx, gy, y, acc, d, slope, gain, want_planes):
+        gy, acc, d = _c(gy), _c(acc), _c(d)
+        require_cuda(gy, acc, d)
+        B, C = gy.shape[0], gy.shape[-1]
+        P = gy.numel() // max(B * C, 1)
+        gacc = torch.empty_like(gy)
+        gd = torch.empty((B, C), dtype=torch.float32, device=gy.device)
+        if y is None:
+            check(lib.gifb200_scale_bwd(ptr(gy), ptr(acc), ptr(d), ptr(gacc), ptr(gd), B, P, C, 0, stream()), "gifb200_scale_bwd")
+        else:
+            y = _c(y)
+            if want_planes and CONV_IMPL == 3 and C % 32 == 0 and P >= 256:
+                pa = torch.empty((2,) + tuple(gy.shape), dtype=torch.bfloat16, device=gy.device)
+                check(lib.gifb200_tail_bwd_planes(ptr(gy), ptr(y), ptr(acc), ptr(d), None, ptr(gacc), None, ptr(gd), B, P, C,
+                                                  slope, gain, None, ptr(pa), stream()), "gifb200_tail_bwd_planes")
+                gacc._gifb200_planes = (gacc._version, pa)
+            else:
+                rt = tf32_enabled()
+                check(lib.gifb200_tail_bwd(ptr(gy), ptr(y), ptr(acc), ptr(d), None, ptr(gacc), None, ptr(gd), B, P, C, slope, gain,
+                                           int(rt), stream()), "gifb200_tail_bwd")
+                _tag(gacc, rt)
+        ctx.save_for_backward(gy, y, acc, d)
+        ctx.cfg = (slope, gain, y is not None)
+        ctx.set_materialize_grads(False)
+        return gacc, gd
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gg, ggd):
+        gy, y, acc, d = ctx.saved_tensors
+        slope, gain, has_y = ctx.cfg
+        if gg is None and ggd is None:
+            return None, None, None, None, None, None, None
+        gg = None if gg is None else _c(gg)
+        ggd = None if ggd is None else _c(ggd)
+        B, C = gy.shape[0], gy.shape[-1]
+        P = gy.numel() // max(B * C, 1)
+        ggy = torch.empty_like(gy) if ctx.needs_input_grad[0] else None
+        gx2 = torch.empty_like(gy) if (ctx.needs_input_grad[2] and ggd is not None) else None
+        gdd = torch.empty((B, C), dtype=torch.float32, device=gy.device) if (ctx.needs_input_grad[3] and gg is not None) else None
+        pp = None
+        if ggy is not None and not has_y and CONV_IMPL == 3 and C % 32 == 0 and P >= 256:
+            pp = torch.empty((2,) + tuple(gy.shape), dtype=torch.bfloat16, device=gy.device)   # gy came out of a convolution
+        check(lib.gifb200_tail_bwd2(ptr(gg), ptr(ggd), ptr(gy), ptr(y) if has_y else None, ptr(acc), ptr(d), ptr(ggy), ptr(gx2),
+                                    ptr(gdd), B, P, C, slope, gain, ptr(pp), stream()), "gifb200_tail_bwd2")
+        if pp is not None:
+            ggy._gifb200_planes = (ggy._version, pp)
+        return ggy, None, gx2, gdd, None, None, None
 
 
 class _ActBwd(torch.autograd.Function):
@@ -622,6 +689,9 @@ class _ChanScale(torch.autograd.Function):
             check(lib.gifb200_scale_bwd(ptr(gy), ptr(x), ptr(s), ptr(gx), ptr(gs), B, P, C, int(rt), stream()),
                   "gifb200_scale_bwd")
             return _tag(gx, rt), gs, None
+        if torch.is_grad_enabled() and not _WEIGHT_GRADS[0] and ctx.needs_input_grad[0] and ctx.needs_input_grad[1]:
+            gx, gs = _TailBwdCG.apply(gy, None, x, s, 1.0, 1.0, False)     # one node, fused second-order rule
+            return gx, gs, None
         gx = chan_scale(gy, s, tf32_enabled()) if ctx.needs_input_grad[0] else None
         gs = spatial_dot(gy, x) if ctx.needs_input_grad[1] else None
         return gx, gs, None
@@ -684,6 +754,9 @@ class _ModConvX3(torch.autograd.Function):
         adj = (gy, w, k, _ADJ_MODE[mode], mode == S1, True, in_hw)
         if torch.is_grad_enabled():
             gxs = _Conv.apply(*adj) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+            if not _WEIGHT_GRADS[0] and gxs is not None:
+                gx, gs = _TailBwdCG.apply(gxs, None, x, s, 1.0, 1.0, False)
+                return gx, gs, None, None, None, None
             gx = chan_scale(gxs, s) if ctx.needs_input_grad[0] else None
             gs = spatial_dot(gxs, x) if ctx.needs_input_grad[1] else None
             gw = None

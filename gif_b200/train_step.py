@@ -52,11 +52,10 @@ class GifTrainer:
         self.discriminator = Discriminator(resolution, num_color_chnls=9, channel_multiplier=2).to(device)
         self.g_running = copy.deepcopy(self.generator).train(False)
         g_ratio, d_ratio = 4 / 5, 16 / 17                                        # train.py:365-366
-        cap = device.type == "cuda"     # capturable Adam keeps its step counter on the device (needed for CUDA graphs)
-        self.g_optimizer = torch.optim.Adam(self.generator.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio),
-                                            capturable=cap)
-        self.d_optimizer = torch.optim.Adam(self.discriminator.parameters(), lr=0.002 * d_ratio,
-                                            betas=(0.0, 0.99 ** d_ratio), capturable=cap)
+        # torch.optim.Adam with the step as multi-tensor CUDA launches and the step counter on the device (CUDA graphs)
+        from .optim import FusedAdam
+        self.g_optimizer = FusedAdam(self.generator.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio))
+        self.d_optimizer = FusedAdam(self.discriminator.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio))
         self.g_reducer = FlatGradAllReducer(list(self.generator.parameters()), world_size)
         self.d_reducer = FlatGradAllReducer(list(self.discriminator.parameters()), world_size)
         self.r1_every = r1_every

@@ -146,11 +146,27 @@ int gifb200_scale_bwd(const float* gy, const float* x, const float* s, float* gx
                       int round_tf32, gifb200_stream_t stream);
 /* gifb200_tail_bwd for the bf16x3 mode: gt_planes / gacc_planes (each may be NULL) receive the two-term bf16 expansion
  * (the layout of gifb200_split_bf16) of gt / gacc in the SAME pass -- the operands of the convolution input-gradient and
- * weight-gradient that follow -- and the fp32 outputs gt / gacc may then be NULL (at least one form of gt is required).
+ * weight-gradient that follow -- and the fp32 outputs gt / gacc may then be NULL (one of gt / gt_planes / gacc is required).
  * C % 32 == 0. */
 int gifb200_tail_bwd_planes(const float* gy, const float* y, const float* acc, const float* d, float* gt, float* gacc,
                             float* gb, float* gd, int B, int P, int C, float slope, float gain, void* gt_planes,
                             void* gacc_planes, gifb200_stream_t stream);
+/* Second-order pass of tail_bwd / scale_bwd (the path-length regulariser differentiates a recorded first-order backward;
+ * reference rule: losses.py:102-124 through cl.py:479-486 / cl.py:311-316).  With m = gain*(y>0 ? 1 : slope) (y == NULL:
+ * m = 1, the modulation variant) the first-order map is gacc = gy*m*d[b,c], gd[b,c] = sum_p gy*m*acc; given the upstream
+ * gradients gg (of gacc; may be NULL) and ggd (of gd, (B,C); may be NULL) this writes in one pass
+ *   ggy = m*(gg*d + ggd*acc)  (may be NULL),  gx2 = gy*m*ggd  (w.r.t. acc; may be NULL),  gdd[b,c] = sum_p gg*gy*m  (w.r.t.
+ *   d; may be NULL; OVERWRITTEN).  ggy_planes (may be NULL; C % 32 == 0): the bf16x3 expansion of ggy in the same pass. */
+int gifb200_tail_bwd2(const float* gg, const float* ggd, const float* gy, const float* y, const float* acc, const float* d,
+                      float* ggy, float* gx2, float* gdd, int B, int P, int C, float slope, float gain, void* ggy_planes,
+                      gifb200_stream_t stream);
+/* One Adam step (torch.optim.Adam, no weight decay / amsgrad: train.py:365-382, stepped at train.py:160 and :246) over
+ * ``count`` fp32 tensors given as HOST arrays of device pointers (read during the call): params, grads, first and second
+ * moments, element counts.  ``step`` is ONE device float shared by the tensors: incremented first, then used for the bias
+ * corrections (so a captured CUDA graph advances it on replay).  One launch per 64 tensors. */
+int gifb200_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      const long long* numel, int count, float* step, float lr, float beta1, float beta2, float eps,
+                      gifb200_stream_t stream);
 /* out[b,c] = sum_p a[b,p,c] * b2[b,p,c]  (gradient of chan_scale w.r.t. s). out is OVERWRITTEN. */
 int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream);
 /* y = alpha*a + beta*b (b may be NULL): residual merge (a+b)/sqrt2 of ResBlock.forward (cl.py:817-818),

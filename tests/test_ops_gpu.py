@@ -295,6 +295,68 @@ def test_fused_tail_and_scale_backward(cuda, fp32_mode, c):
         close(g2, r, TOL32, f"closed-set grad[{name}]")
 
 
+@pytest.mark.parametrize("c", [32, 64, 128, 20])
+def test_fused_second_order_tail_and_scale(cuda, fp32_mode, c):
+    """The create_graph backward taken inside ``ops.input_gradient_only()`` (path-length regulariser): one node per tail /
+    modulation with the fused second-order kernel gifb200_tail_bwd2, against torch's own double backward of the same
+    formulas and against this package's closed-set composition (16-byte and scalar kernel variants)."""
+    import contextlib
+    from gif_b200 import ops
+    b, h, w = 3, 13, 11
+    acc = gu.randn((b, h, w, c), 41).to(cuda)
+    d = (gu.rand_uniform((b, c), 42) + 1.5).to(cuda)
+    noise = gu.randn((b, h, w, c), 43).to(cuda)
+    bias = gu.randn((c,), 44).to(cuda)
+    gy = gu.randn((b, h, w, c), 45).to(cuda)
+    r = gu.randn((b, h, w, c), 46).to(cuda)
+    rd = gu.randn((b, c), 47).to(cuda)
+    names = ("gacc", "gd", "d2/dgy", "d2/dacc", "d2/dd")
+
+    def tail(fused, torch_ref=False):
+        a, dd, g = (t.clone().requires_grad_(True) for t in (acc, d, gy))
+        if torch_ref:
+            y = torch.nn.functional.leaky_relu(a * dd[:, None, None, :] + noise + bias, 0.2) * math.sqrt(2.0)
+        else:
+            y = ops.bias_act(a, bias, 0.2, math.sqrt(2.0), rowscale=dd, add=noise)
+        with (ops.input_gradient_only() if fused else contextlib.nullcontext()):
+            ga, gd = torch.autograd.grad(y, (a, dd), g, create_graph=True)
+        return (ga, gd) + torch.autograd.grad((ga * r).sum() + (gd * rd).sum(), (g, a, dd))
+
+    ref = tail(False, torch_ref=True)
+    for name, g1, g2, rr in zip(names, tail(True), tail(False), ref):
+        close(g1, rr, TOL32, f"fused second-order tail {name}")
+        close(g2, rr, TOL32, f"closed-set second-order tail {name}")
+    # one upstream gradient only (the other output unused): the NULL branches of the kernel
+    for use in (0, 1):
+        outs = []
+        for fused in (True, False):
+            a, dd, g = (t.clone().requires_grad_(True) for t in (acc, d, gy))
+            y = ops.bias_act(a, bias, 0.2, math.sqrt(2.0), rowscale=dd, add=noise)
+            with (ops.input_gradient_only() if fused else contextlib.nullcontext()):
+                first = torch.autograd.grad(y, (a, dd), g, create_graph=True)
+            L = (first[0] * r).sum() if use == 0 else (first[1] * rd).sum()
+            outs.append(torch.autograd.grad(L, (g, a, dd), allow_unused=True))
+        for name, g1, g2 in zip(names[2:], *outs):
+            assert (g1 is None) == (g2 is None) or (g1 is None and float(g2.abs().max()) == 0.0), name
+            if g1 is not None and g2 is not None:
+                close(g1, g2, TOL32, f"fused second-order tail, upstream {use}: {name}")
+
+    # the modulation variant (no mask): gx = gxs*s, gs = sum gxs*x
+    s = gu.randn((b, c), 48).to(cuda)
+    gxs0 = gu.randn((b, h, w, c), 49).to(cuda)
+
+    def scale(fused):
+        g, x, ss = (t.clone().requires_grad_(True) for t in (gxs0, acc, s))
+        if fused:
+            gx, gs = ops._TailBwdCG.apply(g, None, x, ss, 1.0, 1.0, False)
+        else:
+            gx, gs = g * ss[:, None, None, :], (g * x).sum((1, 2))
+        return (gx, gs) + torch.autograd.grad((gx * r).sum() + (gs * rd).sum(), (g, x, ss))
+
+    for name, g1, rr in zip(("gx", "gs", "d2/dgxs", "d2/dx", "d2/ds"), scale(True), scale(False)):
+        close(g1, rr, TOL32, f"fused second-order modulation {name}")
+
+
 @pytest.mark.parametrize("c", [32, 64, 128, 512, 20])
 def test_torgb_kernels(cuda, fp32_mode, c):
     """ToRGB contraction y[b,p,k] = sum_i x[b,p,i] ws[b,k,i]: the 16-byte kernels (8 / 16 / 32 channel lanes, several

@@ -41,11 +41,15 @@ def _err(got, ref_full_or_sample, g, key, sampled):
     return emax, el2
 
 
-def _check(tag, names, tensors, g, tol, report, grad_tol=None):
+def _check(tag, names, tensors, g, tol, report, grad_tol=None, l2_only=None):
     for n, t in zip(names, tensors):
         key = f"{tag}_{n}"
         sampled = (key + "_absmax") in g.files
         emax, el2 = _err(t, g[key], g, key, sampled)
+        if l2_only and n in l2_only:
+            report.append(f"{n} L2 {el2:.1e}/{l2_only[n]:.0e} (max {emax:.1e})")
+            assert el2 < l2_only[n], f"{tag}.{n}: L2 rel {el2:.2e} >= {l2_only[n]:.1e} (max-norm rel {emax:.2e})"
+            continue
         bar = tol if n == "y" else max(grad_tol or tol, 3 * float(g[key + "_floor"]))
         report.append(f"{n} {max(emax, el2):.1e}/{bar:.0e}")
         assert emax < bar and el2 < bar, f"{tag}.{n}: max-norm rel {emax:.2e}, L2 rel {el2:.2e} >= {bar:.1e}"
@@ -166,8 +170,14 @@ def test_noise_injection_tc_shapes(cuda, gold, mode, tol):
         pn = ["noise_conv.0.weight", "noise_conv.0.bias", "noise_conv.2.weight", "noise_conv.4.weight", "noise_conv.4.bias"]
         grads = torch.autograd.grad((y * gy).sum(), [img, cond] + [named[n] for n in pn])
         rep = []
-        _check("ni", ["y", "gimg", "gcond"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep,
-               grad_tol=5e-2 if mode == "tf32" else None)      # gradients through the two ReLUs: see test_res_block_tc_shapes
+        # Gradients that pass BACK through the ReLUs (w.r.t. the condition and the first two convolutions): a forward error
+        # eps flips the mask of ~eps of the pre-activations and each flip switches a whole pixel's contribution on or off, so
+        # the L2 error follows sqrt(eps) whatever the arithmetic (measured: bf16x3 4.5e-3, tf32 3.1e-2) and the max-norm is
+        # one flipped pixel.  Bar: L2 <= 3*sqrt(forward bar).  The image gradient and the last convolution's do not cross a
+        # ReLU backwards and keep the operator bar.
+        relu_bar = 3 * (2 * tol) ** 0.5
+        through_relu = {n: relu_bar for n in ["gcond", "g_noise_conv.0.weight", "g_noise_conv.0.bias", "g_noise_conv.2.weight"]}
+        _check("ni", ["y", "gimg", "gcond"] + ["g_" + n for n in pn], [y] + list(grads), gold, 2 * tol, rep, l2_only=through_relu)
         print(f"ni [{mode}]: " + "  ".join(rep))
     finally:
         ops.set_precision("tf32")

@@ -16,7 +16,7 @@ from gif_b200.train_step import GifTrainer  # noqa: E402
 
 def main(kind):
     dev = torch.device("cuda:0")
-    ops.set_precision("tf32")
+    ops.set_precision(os.environ.get("GIFB200_PROBE_PRECISION", "bf16x3"))
     B, R = 32, 256
     tr = GifTrainer(dev, R, ppl=(kind == "ppl"))
     g = torch.Generator(device=dev).manual_seed(0)
@@ -33,8 +33,8 @@ def main(kind):
         torch.cuda.synchronize()
     ev = [e for e in prof.key_averages() if e.device_time_total > 0]
     tot = sum(e.device_time_total for e in ev)
-    print(f"# {kind} iteration: {sum(e.count for e in ev)} kernels, {tot / 1e3:.2f} ms device time")
-    for e in sorted(ev, key=lambda e: -e.device_time_total)[:45]:
+    print(f"# {kind} iteration [{ops.get_precision()}]: {sum(e.count for e in ev)} kernels, {tot / 1e3:.2f} ms device time")
+    for e in sorted(ev, key=lambda e: -e.device_time_total)[:60]:
         print(f"{e.device_time_total / 1e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count:4d}  avg={e.device_time_total / e.count:8.1f} us  {e.key[:90]}")
 
 
