@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libgifb200.so")
 _p = ctypes.c_void_p
 _i = ctypes.c_int
 _f = ctypes.c_float
+_d = ctypes.c_double
 _ll = ctypes.c_longlong
 _sz = ctypes.c_size_t
 
@@ -39,7 +40,7 @@ SIGNATURES = {
     "gifb200_tail_bwd_planes": (_i, [_p] * 8 + [_i, _i, _i, _f, _f, _p, _p, _p]),
     "gifb200_scale_bwd": (_i, [_p] * 5 + [_i, _i, _i, _i, _p]),
     "gifb200_tail_bwd2": (_i, [_p] * 9 + [_i, _i, _i, _f, _f, _p, _p]),
-    "gifb200_adam_step": (_i, [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _p]),
+    "gifb200_adam_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _d, _d, _d, _d, _p]),
     "gifb200_spatial_dot": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "gifb200_axpby": (_i, [_p, _p, _p, _ll, _f, _f, _i, _p]),
     "gifb200_demod": (_i, [_p, _p, _p, _i, _i, _i, _f, _p]),

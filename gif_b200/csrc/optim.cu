@@ -18,10 +18,13 @@ struct AdamPack {
     const float* g[kAdamPack];
     float* m[kAdamPack];
     float* v[kAdamPack];
+    float* s[kAdamPack];      // per-tensor step counters (0-d device floats, torch's capturable layout)
     long long n[kAdamPack];
 };
 
-__global__ void adam_tick_kernel(float* __restrict__ step) { *step += 1.f; }
+__global__ void adam_tick_kernel(const AdamPack pk, int k) {
+    if (threadIdx.x < k) *pk.s[threadIdx.x] += 1.f;
+}
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float w1, float beta2, float omb2, float neg_step_size,
                                          float bc2_sqrt, float eps) {
@@ -32,21 +35,22 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
     p = __fadd_rn(p, __fmul_rn(neg_step_size, __fdiv_rn(m, denom)));                        // addcdiv_(m, denom, -step_size)
 }
 
-__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamPack pk, const float* __restrict__ step, float lr, float beta1,
-                                                         float beta2, float eps) {
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamPack pk, double lr, double beta1, double beta2_d, float eps) {
     const int t = blockIdx.y;
     const long long n = pk.n[t];
     float* __restrict__ p = pk.p[t];
     const float* __restrict__ g = pk.g[t];
     float* __restrict__ m = pk.m[t];
     float* __restrict__ v = pk.v[t];
-    const double st = static_cast<double>(*step);
-    const double bc1 = 1.0 - pow(static_cast<double>(beta1), st);
-    const double bc2 = 1.0 - pow(static_cast<double>(beta2), st);
-    const float neg_step_size = static_cast<float>(-(static_cast<double>(lr) / bc1));
+    const double st = static_cast<double>(*pk.s[t]);
+    // the hyper-parameters arrive as doubles (python floats in torch): 1 - beta2 taken from a float beta2 is off by 4e-6
+    const double bc1 = 1.0 - pow(beta1, st);
+    const double bc2 = 1.0 - pow(beta2_d, st);
+    const float neg_step_size = static_cast<float>(-(lr / bc1));
     const float bc2_sqrt = static_cast<float>(sqrt(bc2));
-    const float w1 = static_cast<float>(1.0 - static_cast<double>(beta1));
-    const float omb2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+    const float w1 = static_cast<float>(1.0 - beta1);
+    const float omb2 = static_cast<float>(1.0 - beta2_d);
+    const float beta2 = static_cast<float>(beta2_d);
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -81,30 +85,32 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamPack pk, cons
 using namespace gifb200;
 
 extern "C" int gifb200_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                                 const long long* numel, int count, float* step, float lr, float beta1, float beta2, float eps,
-                                 gifb200_stream_t stream) {
-    GIFB200_REQUIRE(count >= 0 && step, GIFB200_E_SHAPE, "adam_step: bad arguments");
-    GIFB200_REQUIRE(count == 0 || (params && grads && exp_avg && exp_avg_sq && numel), GIFB200_E_SHAPE, "adam_step: null table");
+                                 float* const* steps, const long long* numel, int count, double lr, double beta1, double beta2,
+                                 double eps, gifb200_stream_t stream) {
+    GIFB200_REQUIRE(count >= 0, GIFB200_E_SHAPE, "adam_step: bad arguments");
+    GIFB200_REQUIRE(count == 0 || (params && grads && exp_avg && exp_avg_sq && steps && numel), GIFB200_E_SHAPE,
+                    "adam_step: null table");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    adam_tick_kernel<<<1, 1, 0, st>>>(step);
-    GIFB200_LAUNCH_CHECK("adam_tick_kernel");
     for (int base = 0; base < count; base += kAdamPack) {
         AdamPack pk;
         memset(&pk, 0, sizeof(pk));
         const int k = (count - base < kAdamPack) ? count - base : kAdamPack;
         long long nmax = 0;
         for (int i = 0; i < k; ++i) {
-            GIFB200_REQUIRE(params[base + i] && grads[base + i] && exp_avg[base + i] && exp_avg_sq[base + i] && numel[base + i] >= 0,
-                            GIFB200_E_SHAPE, "adam_step: null tensor");
+            GIFB200_REQUIRE(params[base + i] && grads[base + i] && exp_avg[base + i] && exp_avg_sq[base + i] && steps[base + i] &&
+                                numel[base + i] >= 0, GIFB200_E_SHAPE, "adam_step: null tensor");
             pk.p[i] = params[base + i]; pk.g[i] = grads[base + i]; pk.m[i] = exp_avg[base + i]; pk.v[i] = exp_avg_sq[base + i];
+            pk.s[i] = steps[base + i];
             pk.n[i] = numel[base + i];
             if (pk.n[i] > nmax) nmax = pk.n[i];
         }
+        adam_tick_kernel<<<1, kAdamPack, 0, st>>>(pk, k);
+        GIFB200_LAUNCH_CHECK("adam_tick_kernel");
         if (nmax == 0) continue;
         long long bx = (nmax + 256LL * 4 * 8 - 1) / (256LL * 4 * 8);      // ~8 float4 per thread on the largest tensor
         if (bx < 1) bx = 1;
         if (bx > 128) bx = 128;
-        adam_multi_kernel<<<dim3(static_cast<unsigned>(bx), k), 256, 0, st>>>(pk, step, lr, beta1, beta2, eps);
+        adam_multi_kernel<<<dim3(static_cast<unsigned>(bx), k), 256, 0, st>>>(pk, lr, beta1, beta2, static_cast<float>(eps));
         GIFB200_LAUNCH_CHECK("adam_multi_kernel");
     }
     return GIFB200_OK;

@@ -162,10 +162,12 @@ int gifb200_tail_bwd2(const float* gg, const float* ggd, const float* gy, const 
                       gifb200_stream_t stream);
 /* One Adam step (torch.optim.Adam, no weight decay / amsgrad: train.py:365-382, stepped at train.py:160 and :246) over
  * ``count`` fp32 tensors given as HOST arrays of device pointers (read during the call): params, grads, first and second
- * moments, element counts.  ``step`` is ONE device float shared by the tensors: incremented first, then used for the bias
- * corrections (so a captured CUDA graph advances it on replay).  One launch per 64 tensors. */
+ * moments, per-tensor step counters (0-d device floats, the layout of torch's capturable Adam), element counts.  Each
+ * counter is incremented on the device first, then used for the bias corrections (a captured CUDA graph advances it on
+ * replay).  The hyper-parameters are doubles (python floats in torch: 1 - beta2 must not be taken from a float beta2).
+ * Two launches per 64 tensors.  The caller owns autograd's version counters of the parameters (raw pointer writes). */
 int gifb200_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                      const long long* numel, int count, float* step, float lr, float beta1, float beta2, float eps,
+                      float* const* steps, const long long* numel, int count, double lr, double beta1, double beta2, double eps,
                       gifb200_stream_t stream);
 /* out[b,c] = sum_p a[b,p,c] * b2[b,p,c]  (gradient of chan_scale w.r.t. s). out is OVERWRITTEN. */
 int gifb200_spatial_dot(const float* a, const float* b2, float* out, int B, int P, int C, gifb200_stream_t stream);

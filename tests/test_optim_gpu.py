@@ -44,6 +44,11 @@ def test_fused_adam_follows_torch_adam(cuda, betas):
         sa, sb = o.state[a], r.state[b]
         assert _rel(sa["exp_avg"], sb["exp_avg"]) < 1e-6 and _rel(sa["exp_avg_sq"], sb["exp_avg_sq"]) < 1e-6
     assert float(o.state[ours[0]]["step"]) == 6.0 and float(r.state[ref[0]]["step"]) == 6.0
+    assert float(o.state[ours[4]]["step"]) == 5.0          # skipped once: the counter is per parameter, like torch's
+    v0 = ours[0]._version
+    _set_grads(ours, 999)
+    o.step()
+    assert ours[0]._version > v0                           # raw-pointer update is visible to autograd's version counters
 
 
 def test_fused_adam_state_dict_round_trips_with_torch_adam(cuda):
@@ -56,11 +61,12 @@ def test_fused_adam_state_dict_round_trips_with_torch_adam(cuda):
         _set_grads(a, 200 + it)
         fa.step()
     tb = torch.optim.Adam(b, lr=1e-3, betas=(0.0, 0.99), foreach=False)
-    sd = fa.state_dict()
+    import copy
+    sd = copy.deepcopy(fa.state_dict())                  # what a file round trip gives (load_state_dict itself aliases tensors)
     sd["param_groups"][0]["capturable"] = False          # the reference's optimiser is a plain one
     tb.load_state_dict(sd)
     fc = FusedAdam(c, lr=1e-3, betas=(0.0, 0.99))
-    fc.load_state_dict(tb.state_dict())
+    fc.load_state_dict(copy.deepcopy(tb.state_dict()))
     with torch.no_grad():
         for x, y, z in zip(a, b, c):
             y.copy_(x)
