@@ -87,7 +87,12 @@ __device__ __forceinline__ bool eval0(const Setup0& s, int px, int py, float& w0
     w2 = u;
     if (!(w2 >= 0.f && w1 >= 0.f && w0 > 0.f)) return false;
     const float t = __fadd_rn(__fadd_rn(__fdiv_rn(w0, s.z0), __fdiv_rn(w1, s.z1)), __fdiv_rn(w2, s.z2));
-    zp = __double2float_rn(__ddiv_rn(1.0, static_cast<double>(t)));   // '1.' is a double literal in the reference
+    // The reference divides in double ('1.' is a double literal, :148) and rounds the quotient to float.  For a quotient of
+    // two binary32 numbers, rounding first to binary64 (53 bits >= 2*24 + 2) and then to binary32 gives the correctly rounded
+    // binary32 quotient (double rounding is innocuous for +,-,*,/ when the wide format has >= 2p+2 digits -- Figueroa), so
+    // the IEEE single-precision division below returns the same bits without the fp64 division sequence; the bit-exactness
+    // tests against the host build of the reference kernel cover it.
+    zp = __fdiv_rn(1.f, t);
     return true;
 }
 
@@ -279,7 +284,8 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
     __shared__ SetupT s_setup[256];
     __shared__ int s_incl[256];                 // inclusive prefix of the fragment counts
     __shared__ int s_face[256];
-    __shared__ unsigned int s_box[256];         // xa | ya << 8 | width << 16  (tile-relative, all < 256)
+    __shared__ unsigned int s_box[256];         // xa | ya << 4 | (width-1) << 8 | ceil(4096/width) << 12  (tile-relative)
+    __shared__ unsigned char s_coarse[2048];    // record holding fragment 32*k: entry point of the per-fragment search
     __shared__ int s_warp[8];
     const int gbin = blockIdx.x;
     const int b = gbin / g.nbins, bin = gbin - b * g.nbins;
@@ -316,9 +322,10 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
                 if (xa <= xb && ya <= yb) {
                     s_setup[t] = setup_any<CONV>(fc);
                     s_face[t] = f;
-                    s_box[t] = static_cast<unsigned int>(xa - tx0) | (static_cast<unsigned int>(ya - ty0) << 8) |
-                               (static_cast<unsigned int>(xb - xa + 1) << 16);
-                    cnt = (xb - xa + 1) * (yb - ya + 1);
+                    const unsigned int wd = static_cast<unsigned int>(xb - xa + 1);          // 1..16
+                    s_box[t] = static_cast<unsigned int>(xa - tx0) | (static_cast<unsigned int>(ya - ty0) << 4) | ((wd - 1u) << 8) |
+                               (((4096u + wd - 1u) / wd) << 12);
+                    cnt = static_cast<int>(wd) * (yb - ya + 1);
                 }
             }
         }
@@ -337,21 +344,21 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
             if (k < wid) woff += v;
             total += v;
         }
-        s_incl[t] = incl + woff;
+        incl += woff;
+        s_incl[t] = incl;
+        // coarse index: the record that holds fragment 32*k (records are at most 256 fragments: <= 8 entries each, usually 0-1)
+        for (int k = (incl - cnt + 31) >> 5; (k << 5) < incl; ++k) s_coarse[k] = static_cast<unsigned char>(t);
         __syncthreads();
         for (int wk = t; wk < total; wk += 256) {
-            int lo = 0, hi = 255;                         // first record whose inclusive prefix exceeds wk
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int mid = (lo + hi) >> 1;
-                if (s_incl[mid] > wk) hi = mid; else lo = mid + 1;
-            }
-            const int r = lo;
+            int r = s_coarse[wk >> 5];                    // first record whose inclusive prefix exceeds wk: a short walk
+            int prev = r ? s_incl[r - 1] : 0, cur = s_incl[r];
+            while (cur <= wk) { prev = cur; cur = s_incl[++r]; }
             const unsigned int box = s_box[r];
-            const int wd = static_cast<int>(box >> 16);
-            const int local = wk - (r ? s_incl[r - 1] : 0);
-            const int ry = local / wd, rx = local - ry * wd;
-            const int lx = static_cast<int>(box & 255u) + rx, ly = static_cast<int>((box >> 8) & 255u) + ry;
+            const int wd = static_cast<int>((box >> 8) & 15u) + 1;
+            const int local = wk - prev;                  // < 256
+            // local / wd without a division: (local * ceil(4096/wd)) >> 12 is exact for local < 256, wd <= 16
+            const int ry = static_cast<int>((static_cast<unsigned int>(local) * (box >> 12)) >> 12), rx = local - ry * wd;
+            const int lx = static_cast<int>(box & 15u) + rx, ly = static_cast<int>((box >> 4) & 15u) + ry;
             float w0, w1, w2, zp;
             if (!eval_any<CONV>(s_setup[r], tx0 + lx, ty0 + ly, g.w, g.h, w0, w1, w2, zp) || !(zp == zp)) continue;
             const unsigned long long k = make_key(zp, s_face[r]);

@@ -65,9 +65,12 @@ extern "C" int gifb200_sgemm(int transA, int transB, int M, int N, int K, float 
     // few output tiles and a long K (the 8192 -> 512 discriminator head, its gradients): split K across CTAs
     const long long tiles = static_cast<long long>(cdiv(N, 32)) * cdiv(M, 32);
     int splits = 1;
-    if (tiles < kNumSMs && K >= 1024) {
+    // ... and the batch-32 style / mapping-network GEMMs (M = 32, N = K = 512: 16 output tiles, 16 serial k-tiles each was
+    // 27 us of latency per launch, 250 launches per step): at least two k-tiles per split
+    if (tiles < kNumSMs && K >= 128 && ldc == N) {
         splits = static_cast<int>((2LL * kNumSMs + tiles - 1) / tiles);
-        if (splits > K / 256) splits = K / 256;
+        const int max_splits = K >= 1024 ? K / 256 : K / 64;
+        if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
     }
     int kps = ((K + splits - 1) / splits + 31) / 32 * 32;

@@ -811,7 +811,11 @@ class _Axpby(torch.autograd.Function):
         alpha, beta, has_b = ctx.cfg
         rt = tf32_enabled()
         ga = _tag(_Axpby.apply(g, None, alpha, 0.0, rt), rt) if ctx.needs_input_grad[0] else None
-        gb = _tag(_Axpby.apply(g, None, beta, 0.0, rt), rt) if (has_b and ctx.needs_input_grad[1]) else None
+        if has_b and ctx.needs_input_grad[1]:
+            # the residual merge (a + b)/sqrt2 has alpha == beta: both branches receive the same tensor, computed once
+            gb = ga if (ga is not None and alpha == beta) else _tag(_Axpby.apply(g, None, beta, 0.0, rt), rt)
+        else:
+            gb = None
         return ga, gb, None, None, None
 
 
