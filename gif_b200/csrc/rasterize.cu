@@ -273,7 +273,7 @@ template <> __device__ __forceinline__ Setup1 setup_any<1>(const float* __restri
 // triangle sizes are (the first version gave each triangle 4 lanes that walked its bbox: ncu showed 3-4 of 32 lanes
 // active in the fragment loop and 45% of all warp samples waiting at the barrier behind the few busy warps).
 template <int CONV>
-__global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
+__global__ void __launch_bounds__(256, 8) raster_tile_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
                                                           const float* __restrict__ colors2, float* __restrict__ depth,
                                                           int* __restrict__ tri, float* __restrict__ out3,
                                                           float* __restrict__ out3b, RasterGeom g,
@@ -287,9 +287,11 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
     __shared__ unsigned int s_box[256];         // xa | ya << 4 | (width-1) << 8 | ceil(4096/width) << 12  (tile-relative)
     __shared__ unsigned char s_coarse[2048];    // record holding fragment 32*k: entry point of the per-fragment search
     __shared__ int s_warp[8];
-    const int gbin = blockIdx.x;
-    const int b = gbin / g.nbins, bin = gbin - b * g.nbins;
-    const int by = bin / g.bins_x, bx = bin - by * g.bins_x;
+    const int bx = blockIdx.x, by = blockIdx.y, b = blockIdx.z;      // 3-D grid: no per-thread integer divisions
+    const int gbin = (b * g.bins_y + by) * g.bins_x + bx;
+    const bool brute = overflow[b] != 0;
+    const int n = brute ? g.F : count[gbin];
+    if (n == 0) return;                                              // empty tile (uniform per CTA): buffers keep their values
     const int tx0 = bx * TILE, ty0 = by * TILE;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int px = tx0 + (t & (TILE - 1)), py = ty0 + (t >> 4);
@@ -305,8 +307,6 @@ __global__ void __launch_bounds__(256) raster_tile_kernel(const float* __restric
         key[t] = k0;
     }
     // phase 1: triangles -> fragments -> shared-memory depth test
-    const bool brute = overflow[b] != 0;
-    const int n = brute ? g.F : count[gbin];
     const int* lst = list + (brute ? 0 : offset[gbin]);
     const float* fvb = fv + static_cast<long long>(b) * g.F * 9;
     for (int base = 0; base < n; base += 256) {
@@ -404,7 +404,7 @@ struct Moments {
 };
 
 template <int CONV>
-__global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
+__global__ void __launch_bounds__(128, 8) raster_bwd_face_kernel(const float* __restrict__ fv, const float* __restrict__ colors,
                                                               const float* __restrict__ colors2, const int* __restrict__ tri,
                                                               const float* __restrict__ g_bary, const float* __restrict__ g_img,
                                                               const float* __restrict__ g_img2, const float* __restrict__ g_depth,
@@ -448,12 +448,28 @@ __global__ void __launch_bounds__(128) raster_bwd_face_kernel(const float* __res
     if (live && tri_bbox<CONV>(fc, w, h, xmin, xmax, ymin, ymax)) {
         const long long img = static_cast<long long>(b) * h * w;
         const int bw = xmax - xmin + 1, area = bw * (ymax - ymin + 1);
-        for (int pi = sub; pi < area; pi += kBwdLanes) {
-            {
-                const int ry = pi / bw;
-                const int y = ymin + ry, x = xmin + (pi - ry * bw);
+        // four triangle-buffer reads in flight per lane before the first ownership test (the loop is a chain of dependent
+        // global round trips: ownership read -> gradient reads), same accumulation order as a plain loop
+        for (int p0 = sub; p0 < area; p0 += kBwdLanes * 4) {
+            int own[4];
+            unsigned int xy[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pi = p0 + u * kBwdLanes;
+                own[u] = -2;                                  // never a face index (faces >= 0, empty pixels -1)
+                xy[u] = 0u;
+                if (pi < area) {
+                    const int ry = pi / bw;
+                    const int y = ymin + ry, x = xmin + (pi - ry * bw);
+                    xy[u] = static_cast<unsigned int>(x) | (static_cast<unsigned int>(y) << 16);   // h, w <= 65535
+                    own[u] = tri[img + static_cast<long long>(y) * w + x];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (own[u] != f) continue;
+                const int x = static_cast<int>(xy[u] & 0xffffu), y = static_cast<int>(xy[u] >> 16);
                 const long long pix = img + static_cast<long long>(y) * w + x;
-                if (tri[pix] != f) continue;
                 float qx, qy;
                 if (CONV == 0) { qx = x - x0; qy = y - y0; }
                 else { qx = -1.f + (2 * (w - 1 - x) + 1.0f) / w; qy = -1.f + (2 * (h - 1 - y) + 1.0f) / h; }
@@ -641,8 +657,16 @@ static int rasterize_fwd_impl(const float* face_vertices, const float* face_colo
     GIFB200_LAUNCH_CHECK("bin_scan_kernel");
     bin_kernel<1, CONV><<<cdiv(ntri, 256), 256, 0, st>>>(face_vertices, g, count, offset, list, capacity, overflow);
     GIFB200_LAUNCH_CHECK("bin_kernel<fill>");
-    raster_tile_kernel<CONV><<<static_cast<unsigned int>(nb), 256, 0, st>>>(face_vertices, face_colors, face_colors2, depth,
-                                                                            triangle, out3, out3b, g, count, offset, list, overflow);
+    GIFB200_REQUIRE(g.bins_y <= 65535 && B <= 65535, GIFB200_E_SHAPE, "rasterize: grid too large");
+    // The tile kernel is latency-bound (a CTA's life is a chain of ~6 dependent global round trips: list -> vertices -> ... ->
+    // winner's attributes): 8 CTAs of 32 registers per SM instead of 5, with the shared-memory carveout that lets them fit
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        cudaFuncSetAttribute(raster_tile_kernel<CONV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
+    raster_tile_kernel<CONV><<<dim3(g.bins_x, g.bins_y, B), 256, 0, st>>>(face_vertices, face_colors, face_colors2, depth,
+                                                                          triangle, out3, out3b, g, count, offset, list, overflow);
     GIFB200_LAUNCH_CHECK("raster_tile_kernel");
     return GIFB200_OK;
 }
@@ -674,7 +698,7 @@ extern "C" int gifb200_rasterize_bwd_ex(const float* face_vertices, const float*
                                         const float* g_depth, float* g_face_vertices, float* g_face_colors,
                                         float* g_face_colors2, int B, int F, int h, int w, int convention,
                                         gifb200_stream_t stream) {
-    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0, GIFB200_E_SHAPE, "rasterize_bwd: bad shape");
+    GIFB200_REQUIRE(B >= 0 && F >= 0 && h > 0 && w > 0 && h <= 65535 && w <= 65535, GIFB200_E_SHAPE, "rasterize_bwd: bad shape");
     GIFB200_REQUIRE(convention == 0 || convention == 1, GIFB200_E_SHAPE, "rasterize_bwd: convention must be 0 or 1");
     GIFB200_REQUIRE(g_face_vertices != nullptr, GIFB200_E_SHAPE, "rasterize_bwd: g_face_vertices is required");
     GIFB200_REQUIRE(!g_img || face_colors, GIFB200_E_SHAPE, "rasterize_bwd: g_img needs face_colors");
