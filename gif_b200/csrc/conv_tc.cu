@@ -55,6 +55,9 @@ struct TcParams {
     int tap_dx[4][kMaxTaps];    // input column = site_x + tap_dx        (S2: column in the W/2 space)
     int tap_par[4][kMaxTaps];   // S2: W parity plane
     int in_sy;
+    int ksplit;             // > 1: the K loop (taps x channel chunks) of every tile is cut into ksplit ranges, one tile each,
+    float* part;            //      whose accumulators go to part[ks][...] (same indexing as y); splitk_reduce_kernel sums them
+    long long part_stride;  //      in a fixed order and applies the epilogue (small layers: 16 output tiles cannot fill 148 SMs)
     ConvEpilogue epi;
 };
 
@@ -143,13 +146,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mt, nblk, phase;
-            decode_tile(tile, nblocks, p.nphase, rot_div, mt, nblk, phase);
+            const int ks = tile % p.ksplit;
+            decode_tile(tile / p.ksplit, nblocks, p.nphase, rot_div, mt, nblk, phase);
             int m = mt;
             const int tx = m % p.tiles_x; m /= p.tiles_x;
             const int ty = m % p.tiles_y; m /= p.tiles_y;
             const int n0 = m * p.nt, y0 = ty * p.ht, x0 = tx * p.wt;
             const int iters = p.phase_ntaps[phase] * kchunks;
-            for (int it = 0; it < iters; ++it) {
+            const int it0 = iters * ks / p.ksplit, it1 = iters * (ks + 1) / p.ksplit;      // the whole loop when ksplit == 1
+            for (int it = it0; it < it1; ++it) {
                 const int tap = it / kchunks, c0 = (it % kchunks) * kBlockK;
                 uint8_t* a_dst = smem + stage * L::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
@@ -193,13 +198,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int mt_, nblk_, phase;
-            decode_tile(tile, nblocks, p.nphase, rot_div, mt_, nblk_, phase);
+            const int ks = tile % p.ksplit;
+            decode_tile(tile / p.ksplit, nblocks, p.nphase, rot_div, mt_, nblk_, phase);
             const int iters = p.phase_ntaps[phase] * kchunks;
+            const int it0 = iters * ks / p.ksplit, it1 = iters * (ks + 1) / p.ksplit;
             const int buf = local & 1;
             mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);     // epilogue has drained this buffer
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
-            for (int it = 0; it < iters; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 mbar_wait(&full_bar[stage], ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                     const uint64_t bl = make_kmajor_sw64_desc(a_addr + kATileBytes + L::kBTileBytes / 2);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        umma_bf16(tmem_d, al + 2 * k, bh + 2 * k, idesc, (it | k) != 0);
+                        umma_bf16(tmem_d, al + 2 * k, bh + 2 * k, idesc, (it != it0) || k != 0);
                         umma_bf16(tmem_d, ah + 2 * k, bl + 2 * k, idesc, 1);
                         umma_bf16(tmem_d, ah + 2 * k, bh + 2 * k, idesc, 1);
                     }
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                     const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kATileBytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 8; ++k)   // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 32 B (>>4 = 2)
-                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it != it0) || k != 0);
                 }
                 umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
                 if (++stage == kStages) { stage = 0; ph ^= 1; }
@@ -238,7 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             int mt, nblk, phase;
-            decode_tile(tile, nblocks, p.nphase, rot_div, mt, nblk, phase);
+            const int ks = tile % p.ksplit;
+            decode_tile(tile / p.ksplit, nblocks, p.nphase, rot_div, mt, nblk, phase);
             int m = mt;
             const int tx = m % p.tiles_x; m /= p.tiles_x;
             const int ty = m % p.tiles_y; m /= p.tiles_y;
@@ -246,7 +254,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
             const int Y = (ty * p.ht + h_in) * p.oys + p.phase_oy0[phase], X = (tx * p.wt + w_in) * p.oxs + p.phase_ox0[phase];
             const bool ok = active && n < p.B && Y < p.Ho && X < p.Wo;
             const int col0 = (BLOCK_N >= 64 ? half * kColsPerWarp : 0);
-            float* dst = y + ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N + col0;
+            float* dst = (p.ksplit > 1 ? p.part + ks * p.part_stride : y) +
+                         ((static_cast<long long>(n) * p.Ho + Y) * p.Wo + X) * p.Co + nblk * BLOCK_N + col0;
             const int buf = local & 1;
             mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
             tcgen05_fence_after();
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ok) {
-                    if (p.epi.act) {
+                    if (p.epi.act && p.ksplit == 1) {      // split-K: the reduction pass applies the epilogue to the sum
                         const int o0 = nblk * BLOCK_N + col0 + c;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(apply_epilogue(p.epi, __uint_as_float(v[j]), o0 + j));
@@ -308,6 +317,40 @@ __global__ void __launch_bounds__(256) stage_weights_kernel(const float* __restr
             out[e] = round_tf32(v);
         }
     }
+}
+
+// y[e] = epilogue(sum_s part[s][e]) in split order (deterministic); n4 = elements / 4, Co % 4 == 0
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ y, long long n4,
+                                                            int ksplit, long long stride, ConvEpilogue epi, int Co) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float4 a = __ldcs(reinterpret_cast<const float4*>(part) + i);
+        for (int s = 1; s < ksplit; ++s) {
+            const float4 b = __ldcs(reinterpret_cast<const float4*>(part + s * stride) + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        const int o = static_cast<int>((i * 4) % Co);
+        a.x = apply_epilogue(epi, a.x, o); a.y = apply_epilogue(epi, a.y, o + 1);
+        a.z = apply_epilogue(epi, a.z, o + 2); a.w = apply_epilogue(epi, a.w, o + 3);
+        reinterpret_cast<float4*>(y)[i] = a;
+    }
+}
+
+// K splits for a layer whose output tiles cannot fill the machine (4x4 / 8x8 layers at batch 32: 16-64 tiles, 144 pipeline
+// iterations each; the stride-2 9x9 layer ran at 10 TFLOP/s, bound by one CTA's TMA issue rate).  Stride-1 / stride-2 modes.
+int pick_ksplit(long long tiles, int iters, int mode) {
+    if (mode == 2 || tiles > kNumSMs / 2 || iters < 8) return 1;
+    long long ks = (2LL * kNumSMs) / tiles;
+    if (ks > iters / 4) ks = iters / 4;
+    if (ks > 16) ks = 16;
+    return ks < 2 ? 1 : static_cast<int>(ks);
+}
+
+void tile_geometry(int B, int Hs, int Ws, int& wt, int& ht, int& nt, long long& mtiles) {
+    wt = Ws < 128 ? Ws : 128;
+    ht = (128 / wt) < Hs ? (128 / wt) : Hs;
+    nt = 128 / (wt * ht);
+    mtiles = static_cast<long long>(Ws / wt) * (Hs / ht) * ((B + nt - 1) / nt);
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -361,7 +404,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb,
         if (e != cudaSuccess) return fail(GIFB200_E_CUDA, "cudaFuncSetAttribute(conv_tc_kernel)", cudaGetErrorString(e));
         attr_set = true;
     }
-    const long long total = static_cast<long long>(mtiles) * (p.Co / BLOCK_N) * p.nphase;
+    const long long total = static_cast<long long>(mtiles) * (p.Co / BLOCK_N) * p.nphase * p.ksplit;
     if (total > 2147483647LL) return fail(GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
     const int grid = total < 2 * kNumSMs ? static_cast<int>(total) : 2 * kNumSMs;   // persistent: <= 2 CTAs per SM
     conv_tc_kernel<BLOCK_N, X3><<<grid, kTcThreads, L::kDynamic, st>>>(ma, ma2, mb, mb2, y, p, mtiles, static_cast<int>(total));
@@ -395,8 +438,28 @@ bool conv2d_tc_supported(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, 
     return true;
 }
 
-size_t conv2d_tc_workspace_bytes(int, int, int, int Ci, int, int, int Co, int k, int, int) {
-    return static_cast<size_t>(k) * k * Co * Ci * sizeof(float) + 256;
+static size_t staged_weight_bytes(int Ci, int Co, int k) {
+    return (static_cast<size_t>(k) * k * Co * Ci * sizeof(float) + 256 + 255) / 256 * 256;
+}
+
+// split-K geometry of a supported shape: the number of splits (1 = none)
+static int ksplit_of(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode) {
+    int Hs, Ws, wt, ht, nt;
+    long long mtiles;
+    site_grid(Hi, Wi, Ho, Wo, mode, Hs, Ws);
+    tile_geometry(B, Hs, Ws, wt, ht, nt, mtiles);
+    const int bn = pick_block_n(Co);
+    if (bn == 0) return 1;
+    return pick_ksplit(mtiles * (Co / bn), k * k * (Ci / kBlockK), mode);
+}
+
+size_t conv2d_tc_workspace_bytes(int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k, int mode, int) {
+    size_t bytes = staged_weight_bytes(Ci, Co, k);
+    if (conv2d_tc_supported(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode)) {
+        const int ks = ksplit_of(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
+        if (ks > 1) bytes += static_cast<size_t>(ks) * B * Ho * Wo * Co * sizeof(float) + 256;     // the partial accumulators
+    }
+    return bytes;
 }
 
 int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Ci, int Ho, int Wo, int Co, int k,
@@ -428,13 +491,16 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     memset(&p, 0, sizeof(p));
     p.B = B; p.Ci = Ci; p.Co = Co; p.Ho = Ho; p.Wo = Wo; p.epi = epi;
     site_grid(Hi, Wi, Ho, Wo, mode, p.Hs, p.Ws);
-    p.wt = p.Ws < 128 ? p.Ws : 128;
-    p.ht = (128 / p.wt) < p.Hs ? (128 / p.wt) : p.Hs;
-    p.nt = 128 / (p.wt * p.ht);
+    long long mtiles;
+    tile_geometry(B, p.Hs, p.Ws, p.wt, p.ht, p.nt, mtiles);
     p.tiles_x = p.Ws / p.wt; p.tiles_y = p.Hs / p.ht;
-    const int tiles_n = (B + p.nt - 1) / p.nt;
-    const long long mtiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_n;
     GIFB200_REQUIRE(mtiles <= 2147483647LL, GIFB200_E_SHAPE, "conv2d_tc: too many tiles");
+    p.ksplit = ksplit_of(B, Hi, Wi, Ci, Ho, Wo, Co, k, mode);
+    if (p.ksplit > 1) {
+        p.part_stride = static_cast<long long>(B) * Ho * Wo * Co;
+        p.part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(reinterpret_cast<char*>(wst) + staged_weight_bytes(Ci, Co, k) - 256) + 255) &
+                                          ~static_cast<uintptr_t>(255));
+    }
     p.s2 = mode == 1;
     p.in_sy = mode == 1 ? 2 : 1;
     const int pad = k / 2;
@@ -495,6 +561,13 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
     }
     if (!x3) { ma2 = ma; mb2 = mb; }
     rc = launch_any(bn, x3, ma, ma2, mb, mb2, y, p, static_cast<int>(mtiles), st);
+    if (rc == GIFB200_OK && p.ksplit > 1) {
+        const long long n4 = p.part_stride / 4;
+        int blocks = cdiv(n4, 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.part, y, n4, p.ksplit, p.part_stride, epi, Co);
+        GIFB200_LAUNCH_CHECK("splitk_reduce_kernel");
+    }
     if (mode != 2 || rc != GIFB200_OK) return rc;
     // ---- T2 border: output row Y = 2*Hi and column X = 2*Wi (the sites y = Hi / x = Wi that the power-of-two site grid does
     // not cover).  Row Y = 2*Hi only sees kernel row kh = 2 applied to input row Hi-1: a 1-D transposed convolution along x;
@@ -513,7 +586,7 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         q.nt = 128 / (q.wt * q.ht);
         q.tiles_x = q.Ws / q.wt; q.tiles_y = q.Hs / q.ht;
         const long long mt_e = static_cast<long long>(q.tiles_x) * q.tiles_y * ((B + q.nt - 1) / q.nt);
-        q.s2 = 0; q.in_sy = 1; q.nphase = 2; q.oys = q.oxs = 2;
+        q.s2 = 0; q.in_sy = 1; q.nphase = 2; q.oys = q.oxs = 2; q.ksplit = 1;
         for (int ph = 0; ph < 2; ++ph) {          // parity along the strip
             q.phase_oy0[ph] = row ? 2 * Hi : ph;
             q.phase_ox0[ph] = row ? ph : 2 * Wi;

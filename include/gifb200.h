@@ -64,7 +64,9 @@ long long gifb200_launch_count(void);
  *           same TMEM accumulator (16 significant operand bits, ~1e-5 relative; 1.5x the tensor work of kind::tf32).
  *           With impl 3, `x` is NOT an fp32 tensor but the planes buffer of gifb200_split_bf16 for the input
  *           (2 x B*Hi*Wi*Ci bf16 = the same number of bytes); w stays fp32 (split while staging).  Same shapes as impl 2.
- * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL).
+ * workspace: gifb200_conv2d_workspace_bytes(...) bytes of device memory (may be 0 / NULL): the staged B operand, followed --
+ *   for layers whose output tiles cannot fill the machine (4x4 / 8x8 at batch 32) -- by the partial accumulators of the
+ *   split-K schedule (summed in a fixed order by a reduction pass that also applies the epilogue: deterministic).
  * Fused epilogue (ConvLayer = EqualConv2d -> FusedLeakyReLU, cl.py:752-799; nn.Conv2d + ReLU of NoiseInjection):
  *     y = lrelu(acc + bias[o], slope) * gain, optionally rounded to tf32;  act == 0 writes the plain accumulator
  *     (bias / slope / gain / round_tf32 ignored).

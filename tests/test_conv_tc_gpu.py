@@ -35,6 +35,8 @@ CASES = [
     (2, 128, 128, 32, 128, 3, 0), (2, 16, 16, 96, 256, 1, 0), (1, 256, 256, 32, 32, 3, 0),
     (2, 16, 16, 32, 32, 3, 1), (3, 4, 4, 64, 64, 3, 1), (1, 64, 64, 32, 128, 3, 1), (2, 8, 32, 32, 32, 3, 1),
     (2, 16, 16, 32, 32, 3, 2), (3, 4, 4, 64, 64, 3, 2), (1, 64, 64, 32, 128, 3, 2), (2, 8, 32, 32, 32, 3, 2),
+    # the small layers of the batch-32 step: 16 / 64 output tiles, run with the split-K schedule (16 / 4 splits)
+    (32, 4, 4, 512, 512, 3, 0), (32, 4, 4, 512, 512, 3, 1), (32, 8, 8, 512, 512, 3, 1),
 ]
 
 
@@ -83,6 +85,41 @@ WG_CASES = [
     # STACK variant (Cs == 32): the zero-padded NoiseInjection convs
     (2, 16, 16, 32, 32, 3, 0), (4, 4, 4, 32, 32, 3, 0), (1, 64, 128, 64, 32, 3, 0), (3, 8, 8, 128, 32, 3, 0),
 ]
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", [(3, 4, 4, 64, 32, 3, 0), (32, 4, 4, 512, 512, 3, 1), (5, 8, 8, 32, 64, 3, 0)])
+def test_splitk_with_fused_epilogue(cuda, B, Hs, Ws, Ci, Co, k, mode, impl):
+    """Split-K layers with the fused bias + leaky-ReLU epilogue: the reduction pass applies it to the summed accumulator
+    (tf32 and bf16x3 kernels vs the exact fp32 SIMT path with the same epilogue)."""
+    from gif_b200 import ops
+    from gif_b200._lib import lib
+    g = torch.Generator(device="cuda").manual_seed(B + Hs + Ci + mode + 11)
+    Hi, Wi = (Hs, Ws) if mode != 1 else (2 * Hs + 1, 2 * Ws + 1)
+    ws_plain = k * k * Co * Ci * 4 + 512
+    assert lib.gifb200_conv2d_workspace_bytes(B, Hi, Wi, Ci, Hs, Ws, Co, k, mode, 0, impl) > ws_plain, "shape is not on the split-K schedule"
+    x = round_tf32(torch.randn(B, Hi, Wi, Ci, device=cuda, generator=g))
+    w = round_tf32(torch.randn(k * k, Co, Ci, device=cuda, generator=g) / math.sqrt(Ci * k * k))
+    bias = torch.randn(Co, device=cuda, generator=g)
+    old = ops.CONV_IMPL
+    try:
+        outs = []
+        for im in (impl, 1):
+            ops.CONV_IMPL = im
+            y, _ = ops._conv_raw(x, w, k, mode, False, False, (Hs, Ws), (bias, 0.2, math.sqrt(2.0), 0))
+            outs.append(y)
+    finally:
+        ops.CONV_IMPL = old
+    torch.cuda.synchronize()
+    e = gu.rel_err(outs[0].cpu().numpy(), outs[1].cpu().numpy())
+    assert e < (2e-5 if impl == 2 else 5e-5), e
+    # deterministic: the partial sums are added in split order
+    ops.CONV_IMPL = impl
+    try:
+        y2, _ = ops._conv_raw(x, w, k, mode, False, False, (Hs, Ws), (bias, 0.2, math.sqrt(2.0), 0))
+    finally:
+        ops.CONV_IMPL = old
+    assert torch.equal(y2, outs[0])
 
 
 @pytest.mark.parametrize("B,Hs,Ws,Ci,Co,k,mode", WG_CASES)
