@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """A few small invocations of the round-2 kernels for `compute-sanitizer` (memcheck / racecheck / synccheck): the bf16x3
-convolution (S1, S2, T2 incl. the border launches), the bf16x3 weight gradient (plain, STACK, HALO), the split pass, the fused
-activation backward with planes, and the rasteriser (tile kernel with shared-memory atomics, per-face backward, both
+convolution (S1, S2, T2 incl. the border launches and the split-K schedule + reduction), the bf16x3 weight gradient (plain,
+STACK, HALO), the split pass, the fused activation backward with planes, the second-order tail node, the multi-tensor Adam,
+the split-K GEMM, and the rasteriser (tile kernel with shared-memory atomics, per-face backward, both
 conventions).  Each result is checked against the exact path so a silent out-of-bounds would also show as a mismatch.
 usage: compute-sanitizer --tool memcheck python tools/sanitizer_cases.py"""
 import math
@@ -58,6 +59,29 @@ b = torch.zeros(128, device=dev, requires_grad=True)
 y = ops.conv2d_bias_act(x, w, b, 3)
 y.square().sum().backward()
 assert all(torch.isfinite(t.grad).all() for t in (x, w, b))
+# second-order tail / modulation node (gifb200_tail_bwd2, vector and scalar variants) as the path-length term drives it
+for c in (64, 20):
+    acc = torch.randn(2, 9, 7, c, device=dev, generator=g).requires_grad_(True)
+    dm = (torch.rand(2, c, device=dev, generator=g) + 1.0).requires_grad_(True)
+    nz = torch.randn(2, 9, 7, c, device=dev, generator=g)
+    bs = torch.randn(c, device=dev, generator=g)
+    gy = torch.randn(2, 9, 7, c, device=dev, generator=g).requires_grad_(True)
+    yy = ops.bias_act(acc, bs, 0.2, math.sqrt(2.0), rowscale=dm, add=nz)
+    with ops.input_gradient_only():
+        ga, gd = torch.autograd.grad(yy, (acc, dm), gy, create_graph=True)
+    (ga.square().sum() + gd.square().sum()).backward()
+    assert all(torch.isfinite(t.grad).all() for t in (acc, dm, gy))
+# multi-tensor Adam (two packs: > 64 tensors, odd sizes, unaligned tails) and the split-K style GEMM (M = 32, K = 512)
+from gif_b200.optim import FusedAdam  # noqa: E402
+ps = [torch.randn(s, device=dev, generator=g).requires_grad_(True) for s in [(33,), (64, 64, 3, 3), (5, 7), (1,)] + [(17,)] * 70]
+opt = FusedAdam(ps, lr=1e-3, betas=(0.0, 0.99))
+for _ in range(2):
+    for q in ps:
+        q.grad = torch.randn(q.shape, device=dev, generator=g)
+    opt.step()
+assert all(torch.isfinite(q).all() for q in ps)
+am, bm = torch.randn(32, 512, device=dev, generator=g), torch.randn(512, 512, device=dev, generator=g)
+assert rel(ops.matmul(am, bm, trans_b=True), am @ bm.t()) < 2e-5
 ops.set_precision("tf32")
 # rasteriser, both conventions, forward + backward
 r = np.random.default_rng(0)
