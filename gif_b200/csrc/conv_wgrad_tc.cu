@@ -38,6 +38,8 @@ struct WgParams {
     int k, pad, s2, flip;
     int halo_bo;            // HALO: put the row phase of the tap's start address into the descriptor's base_offset field
     int pw;                 // pixels per TMA row load (min(Ws, 32)); rows per stage = 32 / pw
+    int mr_s, mr_b;         // narrow images (pw < 32): the S / Bg tensor map's box spans ALL rows of a stage (by rows x bn images),
+                            // one TMA issue per chunk and tap instead of one per row (the 4x4 layers issued 256 loads per stage)
     long long units;        // number of 32-pixel units in the small grid
     int splits;
     long long stride_t, stride_cs, stride_cb;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                         const CUtensorMap* ms_ = pl ? &map_s2 : &map_s;
                         const CUtensorMap* mb_ = pl ? &map_b2 : &map_b;
                         uint8_t* a_pl = a_dst + pl * L::kAPlaneBytes;
-                        if (first) {
+                        if (first && (r == 0 || !p.mr_s)) {
                             for (int c = 0; c < kAChunks; ++c) {
                                 if (STACK)   // chunk kh = S shifted by dy = 1 - kh rows (rows outside the image are zero-filled)
                                     tma_load_4d(a_pl + c * kChunkBytes + r * row_bytes, ms_, &full_bar[stage], 0, x0,
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const __grid_constant_
                                             nb * BLOCK_N + c * 32, x0 - 1, y + (STACK ? 0 : kh - p.pad), n);
                             continue;
                         }
+                        if (r != 0 && p.mr_b) continue;
                         for (int kw = first ? 0 : 1; kw < (first ? 1 : KW); ++kw)
                             for (int c = 0; c < L::kBChunks; ++c) {
                                 uint8_t* dst = b_dst + kw * L::kBBytesPerTap + pl * L::kBPlaneBytes + c * kChunkBytes + r * row_bytes;
@@ -421,7 +424,12 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cs), static_cast<cuuint64_t>(p.Ws), static_cast<cuuint64_t>(p.Hs), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cs) * es, static_cast<cuuint64_t>(p.Ws) * p.Cs * es,
                                        static_cast<cuuint64_t>(p.Hs) * p.Ws * p.Cs * es};
-        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), 1, 1};
+        // narrow images: one box = all rows of a stage (rows consecutive in (n, y): by rows of bn images)
+        const int rows_per_stage = kPix / p.pw;
+        const int by = rows_per_stage < p.Hs ? rows_per_stage : p.Hs, bnimg = rows_per_stage / by;
+        p.mr_s = rows_per_stage > 1;
+        p.mr_b = rows_per_stage > 1 && !p.s2;
+        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), static_cast<cuuint32_t>(by), static_cast<cuuint32_t>(bnimg)};
         int rc = encode_map(&m.s, Sb, 4, dims, strides, box, swz, dt);
         if (rc == GIFB200_OK && x3) rc = encode_map(&m.s2, Sb + s_plane, 4, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
@@ -436,7 +444,10 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cb), static_cast<cuuint64_t>(p.Wb), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(p.Cb) * es, static_cast<cuuint64_t>(p.Wb) * p.Cb * es,
                                        static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * es};
-        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(halo ? kHaloRows : p.pw), 1, 1};
+        const int rows_per_stage = kPix / p.pw;       // mode 0: the big grid is the small grid (Hb == Hs)
+        const int by = rows_per_stage < p.Hs ? rows_per_stage : p.Hs, bnimg = rows_per_stage / by;
+        const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(halo ? kHaloRows : p.pw), static_cast<cuuint32_t>(p.mr_b ? by : 1),
+                                   static_cast<cuuint32_t>(p.mr_b ? bnimg : 1)};
         int rc = encode_map(&m.b, Bb, 4, dims, strides, box, swz, dt);
         if (rc == GIFB200_OK && x3) rc = encode_map(&m.b2, Bb + b_plane, 4, dims, strides, box, swz, dt);
         if (rc != GIFB200_OK) return rc;
