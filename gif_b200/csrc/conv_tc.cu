@@ -170,6 +170,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
                         tma_load_4d(a_dst, &map_a, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
                         if (X3) tma_load_4d(a_dst + kATileBytes / 2, &map_a2, &full_bar[stage], c0, x0 + dx, y0 + dy, n0);
                     }
+                } else if (p.s2 == 2) {
+                    // the nt x ht rows of the tile through ONE 5-D box per plane: traversal stride 2 along the input rows
+                    if (lane == 0) {
+                        const int par = p.tap_par[phase][tap];
+                        tma_load_5d(a_dst, &map_a, &full_bar[stage], c0, par, x0 + dx, y0 * p.in_sy + dy, n0);
+                        if (X3) tma_load_5d(a_dst + kATileBytes / 2, &map_a2, &full_bar[stage], c0, par, x0 + dx, y0 * p.in_sy + dy, n0);
+                    }
                 } else {
                     const int par = p.tap_par[phase][tap];
                     const int row_bytes = p.wt * kBlockK * (X3 ? 2 : 4);
@@ -545,9 +552,16 @@ int conv2d_tc(const float* x, const float* w, float* y, int B, int Hi, int Wi, i
         const cuuint64_t dims[5] = {static_cast<cuuint64_t>(Ci), 2, static_cast<cuuint64_t>((Wi + 1) / 2), static_cast<cuuint64_t>(Hi), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[4] = {static_cast<cuuint64_t>(Ci) * es, static_cast<cuuint64_t>(Ci) * 2 * es,
                                        static_cast<cuuint64_t>(Wi) * Ci * es, static_cast<cuuint64_t>(Hi) * Wi * Ci * es};
-        const cuuint32_t box[5] = {kBlockK, 1, static_cast<cuuint32_t>(p.wt), 1, 1};
-        rc = encode_map(&ma, xb, 5, dims, strides, box, swz, dt);
-        if (rc == GIFB200_OK && x3) rc = encode_map(&ma2, xb + x_plane * es, 5, dims, strides, box, swz, dt);
+        // the whole tile (ht rows 2y + kh of nt images) as one box with traversal stride 2 along H (boxDim counts traversed
+        // elements: 2*ht -> ht rows); the per-row form remains for GIFB200_CONV_S2_ROWS=1 (A/B switch)
+        static const bool per_row = [] { const char* e = getenv("GIFB200_CONV_S2_ROWS"); return e && atoi(e) != 0; }();
+        const bool onebox = !per_row && p.ht * p.nt > 1;
+        if (onebox) p.s2 = 2;
+        const cuuint32_t box[5] = {kBlockK, 1, static_cast<cuuint32_t>(p.wt), static_cast<cuuint32_t>(onebox ? 2 * p.ht : 1),
+                                   static_cast<cuuint32_t>(onebox ? p.nt : 1)};
+        const cuuint32_t estr[5] = {1, 1, 1, static_cast<cuuint32_t>(onebox ? 2 : 1), 1};
+        rc = encode_map(&ma, xb, 5, dims, strides, box, swz, dt, estr);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&ma2, xb + x_plane * es, 5, dims, strides, box, swz, dt, estr);
     }
     if (rc != GIFB200_OK) return rc;
     const int bn = pick_block_n(Co);

@@ -428,7 +428,7 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const int rows_per_stage = kPix / p.pw;
         const int by = rows_per_stage < p.Hs ? rows_per_stage : p.Hs, bnimg = rows_per_stage / by;
         p.mr_s = rows_per_stage > 1;
-        p.mr_b = rows_per_stage > 1 && !p.s2;
+        p.mr_b = rows_per_stage > 1;      // stride-2 modes: the big tensor's rows 2y + kh through a traversal stride of 2
         const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(p.pw), static_cast<cuuint32_t>(by), static_cast<cuuint32_t>(bnimg)};
         int rc = encode_map(&m.s, Sb, 4, dims, strides, box, swz, dt);
         if (rc == GIFB200_OK && x3) rc = encode_map(&m.s2, Sb + s_plane, 4, dims, strides, box, swz, dt);
@@ -455,9 +455,14 @@ int conv2d_wgrad_tc(const float* x, const float* gy, float* gw, int B, int Hi, i
         const cuuint64_t dims[5] = {static_cast<cuuint64_t>(p.Cb), 2, static_cast<cuuint64_t>((p.Wb + 1) / 2), static_cast<cuuint64_t>(p.Hb), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[4] = {static_cast<cuuint64_t>(p.Cb) * es, static_cast<cuuint64_t>(p.Cb) * 2 * es,
                                        static_cast<cuuint64_t>(p.Wb) * p.Cb * es, static_cast<cuuint64_t>(p.Hb) * p.Wb * p.Cb * es};
-        const cuuint32_t box[5] = {32, 1, static_cast<cuuint32_t>(p.pw), 1, 1};
-        int rc = encode_map(&m.b, Bb, 5, dims, strides, box, swz, dt);
-        if (rc == GIFB200_OK && x3) rc = encode_map(&m.b2, Bb + b_plane, 5, dims, strides, box, swz, dt);
+        // rows 2y + kh of a stage through ONE box: traversal stride 2 along H (boxDim counts traversed elements: 2*by -> by rows)
+        const int rows_per_stage = kPix / p.pw;
+        const int by = rows_per_stage < p.Hs ? rows_per_stage : p.Hs, bnimg = rows_per_stage / by;
+        const cuuint32_t box[5] = {32, 1, static_cast<cuuint32_t>(p.pw), static_cast<cuuint32_t>(p.mr_b ? 2 * by : 1),
+                                   static_cast<cuuint32_t>(p.mr_b ? bnimg : 1)};
+        const cuuint32_t estr[5] = {1, 1, 1, static_cast<cuuint32_t>(p.mr_b ? 2 : 1), 1};
+        int rc = encode_map(&m.b, Bb, 5, dims, strides, box, swz, dt, estr);
+        if (rc == GIFB200_OK && x3) rc = encode_map(&m.b2, Bb + b_plane, 5, dims, strides, box, swz, dt, estr);
         if (rc != GIFB200_OK) return rc;
     }
     if (!x3) { m.s2 = m.s; m.b2 = m.b; }

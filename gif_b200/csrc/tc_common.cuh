@@ -136,10 +136,13 @@ inline EncodeTiledFn get_encode() {
 
 inline int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                       const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
-                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
+                      CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, const cuuint32_t* elem_strides = nullptr) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(GIFB200_E_ARCH, "cuTensorMapEncodeTiled driver entry point not available");
+    // elem_strides: traversal stride per dimension (a box of n elements with stride s loads ceil(n / s) of them)
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = enc(map, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
